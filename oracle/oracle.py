@@ -1,0 +1,305 @@
+"""ctypes front for oracle/libbinstats_oracle.so — the CPU restatement of the reference hot path.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs.  Nothing under vaex_b200/ imports this module.
+
+The spec objects below (``scalar``, ``ordinal``, ``agg``) are plain dicts so that the very same specs
+can be handed to the product (vaex_b200) in the parity tests.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+DTYPES = ["float64", "float32", "int64", "int32", "int16", "int8", "uint64", "uint32", "uint16", "uint8", "bool"]
+DTYPE_CODE = {name: i for i, name in enumerate(DTYPES)}
+BINNER_SCALAR, BINNER_ORDINAL = 0, 1
+OPS = {"count": 0, "sum": 1, "sum_moment": 2, "min": 3, "max": 4, "first": 5, "last": 5}
+
+
+def dtype_code(dtype):
+    dtype = np.dtype(dtype)
+    return DTYPE_CODE[dtype.newbyteorder("=").name]
+
+
+def is_swapped(ar):
+    return ar.dtype.byteorder not in ("=", "|") and ar.dtype.byteorder != ("<" if np.little_endian else ">")
+
+
+class _Binner(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("dtype", C.c_int32), ("flip", C.c_int32), ("allow_other", C.c_int32), ("invert", C.c_int32), ("pad_", C.c_int32),
+                ("data", C.c_void_p), ("mask", C.c_void_p), ("vmin", C.c_double), ("vmax", C.c_double), ("bins", C.c_uint64),
+                ("ordinal_count", C.c_int64), ("min_value", C.c_int64)]
+
+
+class _Agg(C.Structure):
+    _fields_ = [("op", C.c_int32), ("dtype", C.c_int32), ("dtype2", C.c_int32), ("flip", C.c_int32), ("invert", C.c_int32), ("use_moment", C.c_int32),
+                ("moment", C.c_uint32), ("pad_", C.c_uint32), ("data", C.c_void_p), ("data2", C.c_void_p), ("mask", C.c_void_p),
+                ("grid", C.c_void_p), ("grid_order", C.c_void_p), ("cell_masked", C.c_void_p)]
+
+
+def build():
+    """Compile the C restatement (gcc only)."""
+    subprocess.check_call(["make", "-C", _HERE, "libbinstats_oracle.so"], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libbinstats_oracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_hash64.restype = C.c_uint64
+        L.orc_hash64.argtypes = [C.c_uint64]
+        L.orc_hash_bits.restype = C.c_uint64
+        L.orc_hash_bits.argtypes = [C.c_int, C.c_uint64]
+        L.orc_bin.restype = C.c_int
+        L.orc_bin.argtypes = [C.POINTER(_Binner), C.c_int, C.POINTER(_Agg), C.c_int, C.c_uint64]
+        L.orc_fill_minmax.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_int]
+        L.orc_fill_first.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+        L.orc_set_create.restype = C.c_void_p
+        L.orc_set_create.argtypes = [C.c_int, C.c_int, C.c_int64]
+        L.orc_set_destroy.argtypes = [C.c_void_p]
+        L.orc_set_from_keys.restype = C.c_void_p
+        L.orc_set_from_keys.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64]
+        for name in ("count", "nan_count", "null_count", "nan_index", "null_index"):
+            f = getattr(L, "orc_set_" + name)
+            f.restype = C.c_int64
+            f.argtypes = [C.c_void_p]
+        L.orc_set_offsets.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_set_update.restype = C.c_int
+        L.orc_set_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_set_key_array.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_set_map_ordinal.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.orc_set_isin.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.orc_set_merge.restype = C.c_int
+        L.orc_set_merge.argtypes = [C.c_void_p, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+# ------------------------------------------------------------------------------------------------
+# spec constructors (shared with the product in parity tests)
+# ------------------------------------------------------------------------------------------------
+def scalar(data, vmin, vmax, bins, mask=None):
+    """BinnerScalar spec; ``mask`` follows numpy (1 = masked)."""
+    return dict(kind="scalar", data=data, mask=mask, vmin=float(vmin), vmax=float(vmax), bins=int(bins))
+
+
+def ordinal(data, count, min_value=0, allow_other=False, invert=False, mask=None):
+    return dict(kind="ordinal", data=data, mask=mask, count=int(count), min_value=int(min_value), allow_other=bool(allow_other), invert=bool(invert))
+
+
+def agg(op, data=None, mask=None, moment=None, order=None):
+    """Aggregator spec; ``mask`` follows the aggregator convention (1 = use the row)."""
+    return dict(op=op, data=data, mask=mask, moment=moment, order=order)
+
+
+def binner_shape(b):
+    return b["bins"] + 3 if b["kind"] == "scalar" else b["count"] + (3 if b["allow_other"] else 2)
+
+
+def upcast(dtype):
+    dtype = np.dtype(dtype).newbyteorder("=")
+    if dtype.kind == "f":
+        return np.dtype("float64")
+    if dtype.kind in "ib":
+        return np.dtype("int64")
+    return np.dtype("uint64")
+
+
+def _ptr(ar):
+    return None if ar is None else ar.ctypes.data
+
+
+def _mask_u8(mask):
+    if mask is None:
+        return None
+    mask = np.ascontiguousarray(mask)
+    return mask.view(np.uint8) if mask.dtype == np.bool_ else mask.astype(np.uint8)
+
+
+def binby(binners, aggs, length=None):
+    """Run Grid::bin_ (agg.hpp:106-137) over one chunk.  Returns a list with, per aggregator, the full
+    grid *with* edge cells, shaped (shape_0, shape_1, ...) (dim 0 = first binner, fastest in memory);
+    first/last return a numpy.ma array like the reference (agg_first.cpp:61-114)."""
+    L = lib()
+    keep = []
+    nb = len(binners)
+    B = (_Binner * max(nb, 1))()
+    shapes = []
+    for i, b in enumerate(binners):
+        data = np.asarray(b["data"])
+        if data.ndim != 1 or not (data.flags.c_contiguous):
+            data = np.ascontiguousarray(data)
+        mask = _mask_u8(b["mask"])
+        keep += [data, mask]
+        B[i].kind = BINNER_SCALAR if b["kind"] == "scalar" else BINNER_ORDINAL
+        B[i].dtype = dtype_code(data.dtype)
+        B[i].flip = int(is_swapped(data))
+        B[i].data = _ptr(data)
+        B[i].mask = _ptr(mask)
+        if b["kind"] == "scalar":
+            B[i].vmin, B[i].vmax, B[i].bins = b["vmin"], b["vmax"], b["bins"]
+        else:
+            B[i].ordinal_count, B[i].min_value = b["count"], b["min_value"]
+            B[i].allow_other, B[i].invert = int(b["allow_other"]), int(b["invert"])
+        shapes.append(binner_shape(b))
+        if length is None:
+            length = len(data)
+    cells = int(np.prod(shapes)) if shapes else 1
+    if length is None:
+        length = 0
+    na = len(aggs)
+    A = (_Agg * max(na, 1))()
+    outs = []
+    for k, a in enumerate(aggs):
+        op = a["op"]
+        data = None if a["data"] is None else np.ascontiguousarray(a["data"])
+        order = None if a.get("order") is None else np.ascontiguousarray(a["order"])
+        mask = _mask_u8(a["mask"])
+        keep += [data, order, mask]
+        dt = np.dtype("int64") if data is None else data.dtype.newbyteorder("=")
+        A[k].op = OPS[op]
+        A[k].dtype = dtype_code(dt)
+        A[k].flip = int(data is not None and is_swapped(data))
+        A[k].data = _ptr(data)
+        A[k].mask = _ptr(mask)
+        if op == "count":
+            grid = np.zeros(cells, np.int64)
+        elif op in ("sum", "sum_moment"):
+            grid = np.zeros(cells, upcast(dt))
+            if op == "sum_moment":
+                A[k].use_moment, A[k].moment = 1, int(a["moment"])
+        elif op in ("min", "max"):
+            grid = np.zeros(cells, dt)
+            L.orc_fill_minmax(A[k].dtype, grid.ctypes.data, cells, int(op == "max"))
+        elif op in ("first", "last"):
+            dt2 = np.dtype("int64") if order is None else order.dtype.newbyteorder("=")
+            grid = np.zeros(cells, dt)
+            grid_order = np.zeros(cells, dt2)
+            cell_masked = np.zeros(cells, np.uint8)
+            A[k].dtype2 = dtype_code(dt2)
+            A[k].invert = int(op == "last")
+            A[k].data2 = _ptr(order)
+            L.orc_fill_first(A[k].dtype, A[k].dtype2, grid.ctypes.data, grid_order.ctypes.data, cell_masked.ctypes.data, cells, A[k].invert)
+            A[k].grid_order = grid_order.ctypes.data
+            A[k].cell_masked = cell_masked.ctypes.data
+            keep += [grid_order, cell_masked]
+            outs.append((grid, cell_masked))
+            A[k].grid = grid.ctypes.data
+            continue
+        else:
+            raise ValueError(op)
+        A[k].grid = grid.ctypes.data
+        outs.append(grid)
+    rc = L.orc_bin(B, nb, A, na, length)
+    if rc == -2:
+        raise RuntimeError("data not set")
+    if rc:
+        raise RuntimeError(f"oracle error {rc}")
+    results = []
+    for o in outs:
+        if isinstance(o, tuple):
+            grid, cm = o
+            results.append(np.ma.array(grid.reshape(shapes, order="F"), mask=cm.astype(bool).reshape(shapes, order="F")))
+        else:
+            results.append(o.reshape(shapes, order="F"))
+    return results
+
+
+def hash64(x):
+    return lib().orc_hash64(int(x) & 0xFFFFFFFFFFFFFFFF)
+
+
+class OrderedSet:
+    """Restatement of vaex.superutils.ordered_set_<dtype> (hash_primitives.hpp:437-725)."""
+
+    def __init__(self, dtype, nmaps=1, limit=-1, _handle=None):
+        self.dtype = np.dtype(dtype)
+        self.nmaps = nmaps
+        self._h = lib().orc_set_create(dtype_code(self.dtype), nmaps, limit) if _handle is None else _handle
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_set_destroy(self._h)
+            self._h = None
+
+    @classmethod
+    def from_keys(cls, keys, null_value=-1, nan_count=0, null_count=0):
+        keys = np.ascontiguousarray(keys)
+        h = lib().orc_set_from_keys(dtype_code(keys.dtype), keys.ctypes.data, len(keys), null_value, nan_count, null_count)
+        if not h:
+            raise RuntimeError("key array does not match the claimed null/nan state")
+        return cls(keys.dtype, 1, _handle=h)
+
+    def update(self, keys, masks=None, start_index=0, return_values=False):
+        keys = np.ascontiguousarray(keys, dtype=self.dtype)
+        masks = _mask_u8(masks)
+        n = len(keys)
+        values = np.zeros(n if return_values else 1, np.int64)
+        map_index = np.zeros(n if return_values else 1, np.int16)
+        rc = lib().orc_set_update(self._h, keys.ctypes.data, _ptr(masks), n, start_index, int(return_values), values.ctypes.data, map_index.ctypes.data)
+        if rc == -3:
+            raise RuntimeError("Cannot combine limit with return_inverse")
+        if return_values:
+            return values, map_index
+
+    def __len__(self):
+        return lib().orc_set_count(self._h)
+
+    count = property(__len__)
+    nan_count = property(lambda self: lib().orc_set_nan_count(self._h))
+    null_count = property(lambda self: lib().orc_set_null_count(self._h))
+    nan_index = property(lambda self: lib().orc_set_nan_index(self._h))
+    null_index = property(lambda self: lib().orc_set_null_index(self._h))
+    has_nan = property(lambda self: self.nan_count > 0)
+    has_null = property(lambda self: self.null_count > 0)
+
+    def offsets(self):
+        out = np.zeros(self.nmaps, np.int64)
+        lib().orc_set_offsets(self._h, out.ctypes.data)
+        return out.tolist()
+
+    def key_array(self):
+        out = np.zeros(len(self), self.dtype)
+        lib().orc_set_key_array(self._h, out.ctypes.data)
+        return out
+
+    def map_ordinal(self, keys):
+        keys = np.ascontiguousarray(keys, dtype=self.dtype)
+        out = np.zeros(len(keys), np.int64)
+        lib().orc_set_map_ordinal(self._h, keys.ctypes.data, len(keys), out.ctypes.data)
+        size = len(self)
+        if size < (1 << 7):
+            return out.astype(np.int8)
+        if size < (1 << 15):
+            return out.astype(np.int16)
+        if size < (1 << 31):
+            return out.astype(np.int32)
+        return out
+
+    def isin(self, keys):
+        keys = np.ascontiguousarray(keys, dtype=self.dtype)
+        out = np.zeros(len(keys), np.uint8)
+        lib().orc_set_isin(self._h, keys.ctypes.data, len(keys), out.ctypes.data)
+        return out.astype(bool)
+
+    def flatten_values(self, values, map_index, out):
+        # hash.hpp:267-288
+        offsets = np.asarray(self.offsets())
+        out[:] = values + offsets[map_index]
+        return out
+
+    def merge(self, others):
+        for o in others:
+            if lib().orc_set_merge(self._h, o._h):
+                raise RuntimeError("cannot merge with an unequal maps")
+
+    def flatten(self):
+        return OrderedSet.from_keys(self.key_array(), self.null_index if self.has_null else -1, self.nan_count, self.null_count)
