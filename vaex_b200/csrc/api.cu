@@ -1,0 +1,781 @@
+// api.cu — the C ABI of libb200agg.so (include/b200agg.h): context/slots, aggregator objects, b200_bin.
+#include <math.h>
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "binby.cuh"
+#include "device_utils.cuh"
+
+namespace b200 {
+
+int set_fill_binner(b200_set *s, DevBinner &b); // hashset.cu
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %s (%s) at %s:%d in `%s`", cudaGetErrorName(e), cudaGetErrorString(e), file, line, what);
+    return B200_ERR_CUDA;
+}
+
+// ---- staging of host chunks -----------------------------------------------------------------------
+int slot_reserve(b200_ctx *ctx, Slot *s, size_t bytes) {
+    if (bytes <= s->stage_cap)
+        return B200_OK;
+    if (s->stage) {
+        B200_CUDA(cudaStreamSynchronize(s->stream));
+        B200_CUDA(cudaFree(s->stage));
+        s->stage = nullptr;
+        s->stage_cap = 0;
+    }
+    size_t cap = align_up(bytes + bytes / 4, 1 << 20);
+    B200_CUDA(cudaMalloc(&s->stage, cap));
+    s->stage_cap = cap;
+    (void)ctx;
+    return B200_OK;
+}
+
+void Stager::plan(const void *p, size_t bytes) {
+    if (!p || memspace == B200_MEM_DEVICE)
+        return;
+    for (auto &e : entries)
+        if (e.host == p) { // the same column used twice (e.g. binby x and sum x) is copied once
+            e.bytes = std::max(e.bytes, bytes);
+            return;
+        }
+    entries.push_back(Entry{p, bytes, nullptr});
+}
+
+int Stager::commit() {
+    if (memspace == B200_MEM_DEVICE || entries.empty())
+        return B200_OK;
+    need = 0;
+    for (auto &e : entries)
+        need += align_up(e.bytes, 256);
+    B200_CHECK(slot_reserve(ctx, slot, need));
+    size_t off = 0;
+    for (auto &e : entries) {
+        e.dev = static_cast<char *>(slot->stage) + off;
+        off += align_up(e.bytes, 256);
+        if (e.bytes)
+            B200_CUDA(cudaMemcpyAsync(e.dev, e.host, e.bytes, cudaMemcpyHostToDevice, slot->stream));
+    }
+    return B200_OK;
+}
+
+const void *Stager::dev(const void *p) const {
+    if (!p || memspace == B200_MEM_DEVICE)
+        return p;
+    for (auto &e : entries)
+        if (e.host == p)
+            return e.dev;
+    return nullptr;
+}
+
+// identity element of an aggregator's device cell
+static uint64_t agg_init_bits(int op, int cell_dtype) {
+    if (op != B200_AGG_MIN && op != B200_AGG_MAX)
+        return 0;
+    const bool mx = op == B200_AGG_MAX;
+    switch (cell_dtype) {
+    case B200_F64: return mx ? 0xfff0000000000000ULL : 0x7ff0000000000000ULL;
+    case B200_F32: return mx ? 0xff800000u : 0x7f800000u;
+    case B200_I64: return mx ? 0x8000000000000000ULL : 0x7fffffffffffffffULL;
+    case B200_U64: return mx ? 0 : ~0ULL;
+    case B200_I32: return mx ? 0x80000000u : 0x7fffffffu;
+    default: return mx ? 0 : 0xffffffffu;
+    }
+}
+
+// reference initial_fill for narrow min/max grids is numeric_limits<T>::min()/max() (src/agg_minmax.cpp:13-18,83-87);
+// the device holds them widened to 32 bit, so untouched cells must come back as the narrow limit.
+static int64_t narrow_limit(int dtype, bool mx) {
+    switch (dtype) {
+    case B200_I16: return mx ? INT16_MIN : INT16_MAX;
+    case B200_I8: return mx ? INT8_MIN : INT8_MAX;
+    case B200_U16: return mx ? 0 : UINT16_MAX;
+    case B200_U8: return mx ? 0 : UINT8_MAX;
+    case B200_BOOL: return mx ? 0 : 1;
+    default: return 0;
+    }
+}
+
+static int agg_fill(b200_agg *a, cudaStream_t st) {
+    if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST) {
+        // src/agg_first.cpp:19-26: value 99, order limits, cell_masked 1; the packed {key,row} state starts at the maximum
+        const int isz = dtype_size(a->dtype), isz2 = dtype_size(a->dtype2);
+        std::vector<unsigned char> v((size_t)a->cells * isz), o((size_t)a->cells * isz2);
+        const bool inv = a->op == B200_AGG_LAST;
+        for (uint64_t i = 0; i < a->cells; i++) {
+            switch (a->dtype) {
+            case B200_F64: reinterpret_cast<double *>(v.data())[i] = 99; break;
+            case B200_F32: reinterpret_cast<float *>(v.data())[i] = 99; break;
+            case B200_BOOL: v[i] = 1; break;
+            default:
+                if (isz == 8)
+                    reinterpret_cast<uint64_t *>(v.data())[i] = 99;
+                else if (isz == 4)
+                    reinterpret_cast<uint32_t *>(v.data())[i] = 99;
+                else if (isz == 2)
+                    reinterpret_cast<uint16_t *>(v.data())[i] = 99;
+                else
+                    v[i] = 99;
+            }
+            switch (a->dtype2) {
+            case B200_F64: reinterpret_cast<double *>(o.data())[i] = inv ? 2.2250738585072014e-308 : 1.7976931348623157e308; break;
+            case B200_F32: reinterpret_cast<float *>(o.data())[i] = inv ? 1.17549435e-38f : 3.40282347e38f; break;
+            case B200_I64: reinterpret_cast<int64_t *>(o.data())[i] = inv ? INT64_MIN : INT64_MAX; break;
+            case B200_I32: reinterpret_cast<int32_t *>(o.data())[i] = inv ? INT32_MIN : INT32_MAX; break;
+            case B200_I16: reinterpret_cast<int16_t *>(o.data())[i] = inv ? INT16_MIN : INT16_MAX; break;
+            case B200_I8: reinterpret_cast<int8_t *>(o.data())[i] = inv ? INT8_MIN : INT8_MAX; break;
+            case B200_U64: reinterpret_cast<uint64_t *>(o.data())[i] = inv ? 0 : UINT64_MAX; break;
+            case B200_U32: reinterpret_cast<uint32_t *>(o.data())[i] = inv ? 0 : UINT32_MAX; break;
+            case B200_U16: reinterpret_cast<uint16_t *>(o.data())[i] = inv ? 0 : UINT16_MAX; break;
+            case B200_U8: o[i] = inv ? 0 : UINT8_MAX; break;
+            default: o[i] = inv ? 0 : 1; break;
+            }
+        }
+        B200_CUDA(cudaMemcpyAsync(a->grid, v.data(), v.size(), cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(a->order, o.data(), o.size(), cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemsetAsync(a->cell_masked, 1, a->cells, st));
+        B200_CUDA(cudaMemsetAsync(a->state, 0xff, a->cells * 16, st));
+        B200_CUDA(cudaStreamSynchronize(st)); // the host vectors die at scope exit
+        return B200_OK;
+    }
+    const uint64_t bits = agg_init_bits(a->op, a->cell_dtype);
+    if (bits == 0)
+        B200_CUDA(cudaMemsetAsync(a->grid, 0, a->cells * dtype_size(a->cell_dtype), st));
+    else
+        B200_CHECK(launch_fill(st, a->grid, a->cell_dtype, a->cells, bits));
+    return B200_OK;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+const char *b200_last_error(void) { return g_err; }
+int b200_abi_version(void) { return B200_ABI_VERSION; }
+
+int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int b200_ctx_create(int device, int nslots, b200_ctx **out) {
+    if (!out || nslots < 1 || nslots > 1024) {
+        set_error("b200_ctx_create: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    int ndev = 0;
+    B200_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) {
+        set_error("b200_ctx_create: device %d not present (%d CUDA devices) — this library has no CPU fallback", device, ndev);
+        return B200_ERR_CUDA;
+    }
+    B200_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B200_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("b200_ctx_create: device %d is sm_%d%d; libb200agg is built for sm_100a only", device, prop.major, prop.minor);
+        return B200_ERR_CUDA;
+    }
+    b200_ctx *ctx = new b200_ctx;
+    ctx->device = device;
+    ctx->nslots = nslots;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    for (int i = 0; i < nslots; i++) {
+        Slot *s = new Slot;
+        B200_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        B200_CUDA(cudaEventCreateWithFlags(&s->h2d_done, cudaEventDisableTiming));
+        B200_CUDA(cudaMallocHost(&s->pinned, 4096));
+        B200_CUDA(cudaMalloc(&s->dscratch, 4096));
+        ctx->slots.push_back(s);
+    }
+    *out = ctx;
+    return B200_OK;
+}
+
+int b200_ctx_destroy(b200_ctx *ctx) {
+    if (!ctx)
+        return B200_OK;
+    cudaSetDevice(ctx->device);
+    for (Slot *s : ctx->slots) {
+        cudaStreamSynchronize(s->stream);
+        cudaFree(s->stage);
+        cudaFree(s->dscratch);
+        cudaFreeHost(s->pinned);
+        cudaEventDestroy(s->h2d_done);
+        cudaStreamDestroy(s->stream);
+        delete s;
+    }
+    delete ctx;
+    return B200_OK;
+}
+
+int b200_ctx_sync(b200_ctx *ctx, int slot) {
+    if (!ctx || slot >= ctx->nslots) {
+        set_error("b200_ctx_sync: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(ctx->device));
+    if (slot < 0) {
+        for (Slot *s : ctx->slots)
+            B200_CUDA(cudaStreamSynchronize(s->stream));
+    } else {
+        B200_CUDA(cudaStreamSynchronize(ctx->slots[slot]->stream));
+    }
+    return B200_OK;
+}
+
+int b200_ctx_device(const b200_ctx *ctx) { return ctx ? ctx->device : -1; }
+
+int b200_ctx_stream(b200_ctx *ctx, int slot, void **stream_out) {
+    if (!ctx || slot < 0 || slot >= ctx->nslots || !stream_out) {
+        set_error("b200_ctx_stream: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    *stream_out = (void *)ctx->slots[slot]->stream;
+    return B200_OK;
+}
+
+// ---- aggregators -----------------------------------------------------------------------------------
+int b200_agg_create(b200_ctx *ctx, int op, int dtype, int dtype2, int byteswap, uint32_t moment, uint64_t cells, b200_agg **out) {
+    if (!ctx || !out || op < B200_AGG_COUNT || op > B200_AGG_LAST || dtype < 0 || dtype >= B200_NDTYPE || dtype2 < 0 || dtype2 >= B200_NDTYPE) {
+        set_error("b200_agg_create: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(ctx->device));
+    b200_agg *a = new b200_agg;
+    a->ctx = ctx;
+    a->op = op;
+    a->dtype = dtype;
+    a->dtype2 = dtype2;
+    a->byteswap = byteswap;
+    a->moment = moment;
+    a->cells = cells;
+    switch (op) {
+    case B200_AGG_COUNT: a->cell_dtype = B200_I64; break;
+    case B200_AGG_SUM:
+    case B200_AGG_SUM_MOMENT: a->cell_dtype = dtype_upcast(dtype); break;
+    case B200_AGG_MIN:
+    case B200_AGG_MAX: a->cell_dtype = dtype_minmax_cell(dtype); break;
+    default: a->cell_dtype = dtype; break;
+    }
+    const size_t n = cells ? cells : 1;
+    cudaError_t e = cudaMalloc(&a->grid, n * dtype_size(a->cell_dtype));
+    if (e == cudaSuccess && (op == B200_AGG_FIRST || op == B200_AGG_LAST)) {
+        e = cudaMalloc(&a->state, n * 16);
+        if (e == cudaSuccess)
+            e = cudaMalloc(&a->order, n * dtype_size(dtype2));
+        if (e == cudaSuccess)
+            e = cudaMalloc((void **)&a->cell_masked, n);
+    }
+    if (e != cudaSuccess) {
+        b200_agg_destroy(a);
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            set_error("b200_agg_create: out of device memory for %llu cells", (unsigned long long)cells);
+            return B200_ERR_NOMEM;
+        }
+        return cuda_fail(e, "cudaMalloc(grid)", __FILE__, __LINE__);
+    }
+    cudaStream_t st = ctx->slots[0]->stream;
+    int rc = agg_fill(a, st);
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess)
+        rc = B200_ERR_CUDA;
+    if (rc) {
+        b200_agg_destroy(a);
+        return rc;
+    }
+    *out = a;
+    return B200_OK;
+}
+
+int b200_agg_destroy(b200_agg *a) {
+    if (!a)
+        return B200_OK;
+    cudaSetDevice(a->ctx->device);
+    cudaFree(a->grid);
+    cudaFree(a->state);
+    cudaFree(a->order);
+    cudaFree(a->cell_masked);
+    delete a;
+    return B200_OK;
+}
+
+int b200_agg_reset(b200_agg *a) {
+    if (!a) {
+        set_error("b200_agg_reset: null");
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(a->ctx->device));
+    B200_CHECK(b200_ctx_sync(a->ctx, -1));
+    cudaStream_t st = a->ctx->slots[0]->stream;
+    B200_CHECK(agg_fill(a, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int b200_agg_reset_on(b200_agg *a, int slot) {
+    if (!a || slot < 0 || slot >= a->ctx->nslots) {
+        set_error("b200_agg_reset_on: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST)
+        return b200_agg_reset(a);
+    B200_CUDA(cudaSetDevice(a->ctx->device));
+    return agg_fill(a, a->ctx->slots[slot]->stream);
+}
+
+int b200_agg_read_on(b200_agg *a, int slot, void *values_out) {
+    if (!a || !values_out || slot < 0 || slot >= a->ctx->nslots) {
+        set_error("b200_agg_read_on: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST) {
+        set_error("b200_agg_read_on: not available for first/last");
+        return B200_ERR_UNSUPPORTED;
+    }
+    B200_CUDA(cudaSetDevice(a->ctx->device));
+    B200_CUDA(cudaMemcpyAsync(values_out, a->grid, a->cells * dtype_size(a->cell_dtype), cudaMemcpyDeviceToHost, a->ctx->slots[slot]->stream));
+    return B200_OK;
+}
+
+uint64_t b200_agg_cells(const b200_agg *a) { return a ? a->cells : 0; }
+
+int b200_agg_result_dtype(const b200_agg *a) {
+    switch (a->op) {
+    case B200_AGG_COUNT: return B200_I64;
+    case B200_AGG_SUM:
+    case B200_AGG_SUM_MOMENT: return dtype_upcast(a->dtype);
+    default: return a->dtype;
+    }
+}
+
+size_t b200_agg_bytes(const b200_agg *a) { return (size_t)dtype_size(b200_agg_result_dtype(a)) * a->cells; }
+int b200_agg_device_dtype(const b200_agg *a) { return a->cell_dtype; }
+
+int b200_agg_device_ptr(b200_agg *a, int which, void **ptr, size_t *bytes) {
+    if (!a || !ptr || which < 0 || which > 1) {
+        set_error("b200_agg_device_ptr: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    if (which == 0) {
+        *ptr = a->grid;
+        if (bytes)
+            *bytes = a->cells * dtype_size(a->cell_dtype);
+    } else {
+        *ptr = a->state;
+        if (bytes)
+            *bytes = a->state ? a->cells * 16 : 0;
+    }
+    return B200_OK;
+}
+
+int b200_agg_read(b200_agg *a, void *values_out, uint8_t *cell_masked_out) {
+    if (!a || !values_out) {
+        set_error("b200_agg_read: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(a->ctx->device));
+    B200_CHECK(b200_ctx_sync(a->ctx, -1));
+    const int rdt = b200_agg_result_dtype(a);
+    const int rsz = dtype_size(rdt), csz = dtype_size(a->cell_dtype);
+    if (!a->cells)
+        return B200_OK;
+    if (rsz == csz) {
+        B200_CUDA(cudaMemcpy(values_out, a->grid, a->cells * rsz, cudaMemcpyDeviceToHost));
+    } else {
+        // narrow min/max grids: 32-bit device cells -> 8/16-bit result; untouched cells map to the narrow limit
+        std::vector<uint32_t> tmp(a->cells);
+        B200_CUDA(cudaMemcpy(tmp.data(), a->grid, a->cells * 4, cudaMemcpyDeviceToHost));
+        const bool mx = a->op == B200_AGG_MAX;
+        const uint32_t init = (uint32_t)agg_init_bits(a->op, a->cell_dtype);
+        const int64_t lim = narrow_limit(a->dtype, mx);
+        for (uint64_t i = 0; i < a->cells; i++) {
+            int64_t v = tmp[i] == init ? lim : (a->cell_dtype == B200_I32 ? (int64_t)(int32_t)tmp[i] : (int64_t)tmp[i]);
+            if (rsz == 2)
+                static_cast<uint16_t *>(values_out)[i] = (uint16_t)v;
+            else
+                static_cast<uint8_t *>(values_out)[i] = (uint8_t)v;
+        }
+    }
+    if (cell_masked_out) {
+        if (a->cell_masked)
+            B200_CUDA(cudaMemcpy(cell_masked_out, a->cell_masked, a->cells, cudaMemcpyDeviceToHost));
+        else
+            memset(cell_masked_out, 0, a->cells);
+    }
+    return B200_OK;
+}
+
+int b200_agg_write(b200_agg *a, const void *values) {
+    if (!a || !values) {
+        set_error("b200_agg_write: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST) {
+        set_error("b200_agg_write: first/last grids cannot be loaded (no order state)");
+        return B200_ERR_UNSUPPORTED;
+    }
+    B200_CUDA(cudaSetDevice(a->ctx->device));
+    B200_CHECK(b200_ctx_sync(a->ctx, -1));
+    const int rsz = dtype_size(b200_agg_result_dtype(a)), csz = dtype_size(a->cell_dtype);
+    if (rsz == csz) {
+        B200_CUDA(cudaMemcpy(a->grid, values, a->cells * rsz, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<uint32_t> tmp(a->cells);
+        for (uint64_t i = 0; i < a->cells; i++) {
+            if (a->cell_dtype == B200_I32)
+                tmp[i] = (uint32_t)(int32_t)(rsz == 2 ? (int32_t) static_cast<const int16_t *>(values)[i] : (int32_t) static_cast<const int8_t *>(values)[i]);
+            else
+                tmp[i] = rsz == 2 ? static_cast<const uint16_t *>(values)[i] : static_cast<const uint8_t *>(values)[i];
+        }
+        B200_CUDA(cudaMemcpy(a->grid, tmp.data(), a->cells * 4, cudaMemcpyHostToDevice));
+    }
+    return B200_OK;
+}
+
+int b200_agg_merge(b200_agg *a, b200_agg *const *others, int nothers) {
+    if (!a || (nothers && !others)) {
+        set_error("b200_agg_merge: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(a->ctx->device));
+    B200_CHECK(b200_ctx_sync(a->ctx, -1));
+    cudaStream_t st = a->ctx->slots[0]->stream;
+    for (int i = 0; i < nothers; i++) {
+        b200_agg *o = others[i];
+        if (o->op != a->op || o->dtype != a->dtype || o->cells != a->cells || o->dtype2 != a->dtype2) {
+            set_error("b200_agg_merge: aggregators differ");
+            return B200_ERR_INVALID;
+        }
+        if (o->ctx != a->ctx)
+            B200_CHECK(b200_ctx_sync(o->ctx, -1));
+        // same-process peers on other devices are read through UVA peer access when enabled; keep it simple: stage through host
+        const void *src = o->grid;
+        void *tmp = nullptr, *tstate = nullptr, *torder = nullptr, *tmask = nullptr;
+        b200_agg view = *o;
+        if (o->ctx->device != a->ctx->device) {
+            const size_t nb = o->cells * dtype_size(o->cell_dtype);
+            B200_CUDA(cudaMalloc(&tmp, nb ? nb : 1));
+            B200_CUDA(cudaMemcpyPeer(tmp, a->ctx->device, o->grid, o->ctx->device, nb));
+            src = tmp;
+            view.grid = tmp;
+            if (o->state) {
+                B200_CUDA(cudaMalloc(&tstate, o->cells * 16));
+                B200_CUDA(cudaMemcpyPeer(tstate, a->ctx->device, o->state, o->ctx->device, o->cells * 16));
+                B200_CUDA(cudaMalloc(&torder, o->cells * dtype_size(o->dtype2)));
+                B200_CUDA(cudaMemcpyPeer(torder, a->ctx->device, o->order, o->ctx->device, o->cells * dtype_size(o->dtype2)));
+                B200_CUDA(cudaMalloc(&tmask, o->cells));
+                B200_CUDA(cudaMemcpyPeer(tmask, a->ctx->device, o->cell_masked, o->ctx->device, o->cells));
+                view.state = tstate;
+                view.order = torder;
+                view.cell_masked = static_cast<uint8_t *>(tmask);
+            }
+        }
+        int rc;
+        if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST)
+            rc = launch_merge_first(st, a, &view);
+        else
+            rc = launch_merge(st, a->op, a->cell_dtype, a->grid, src, a->cells);
+        if (!rc && cudaStreamSynchronize(st) != cudaSuccess)
+            rc = B200_ERR_CUDA;
+        cudaFree(tmp);
+        cudaFree(tstate);
+        cudaFree(torder);
+        cudaFree(tmask);
+        B200_CHECK(rc);
+    }
+    return B200_OK;
+}
+
+// ---- the hot path ----------------------------------------------------------------------------------
+int b200_bin(b200_ctx *ctx, int slot, const b200_binner *binners, int nbinners, const b200_agg_input *aggs, int naggs, int64_t nrows,
+             int64_t row_offset, int memspace, uint32_t flags) {
+    if (!ctx || slot < 0 || slot >= ctx->nslots || nbinners < 0 || nbinners > B200_MAX_BINNERS || naggs < 0 || nrows < 0 || (nbinners && !binners) ||
+        (naggs && !aggs)) {
+        set_error("b200_bin: invalid argument (slot %d of %d, %d binners, %d aggregators, %lld rows)", slot, ctx ? ctx->nslots : 0, nbinners, naggs,
+                  (long long)nrows);
+        return B200_ERR_INVALID;
+    }
+    if (nrows == 0 || naggs == 0)
+        return B200_OK;
+    B200_CUDA(cudaSetDevice(ctx->device));
+
+    // grid layout: first binner fastest (src/agg.hpp:63-73)
+    DevBinner db[B200_MAX_BINNERS];
+    unsigned long long cells = 1;
+    for (int i = 0; i < nbinners; i++) {
+        const b200_binner &b = binners[i];
+        DevBinner &d = db[i];
+        memset(&d, 0, sizeof d);
+        if (b.dtype < 0 || b.dtype >= B200_NDTYPE || !b.data) {
+            set_error("b200_bin: binner %d: %s", i, b.data ? "unknown dtype" : "data not set");
+            return b.data ? B200_ERR_INVALID : B200_ERR_NODATA;
+        }
+        d.kind = b.kind;
+        d.dtype = b.dtype;
+        d.isz = dtype_size(b.dtype);
+        d.byteswap = b.byteswap && d.isz > 1;
+        d.allow_other = b.allow_other;
+        d.invert = b.invert;
+        d.stride = cells;
+        unsigned long long shape;
+        if (b.kind == B200_BINNER_SCALAR) {
+            d.vmin = b.vmin;
+            d.scale = 1. / (b.vmax - b.vmin); // const double scale_v = 1. / (vmax - vmin)  (src/binners.cpp:16)
+            d.bins = b.bins;
+            d.bins_d = (double)b.bins;
+            shape = b.bins + 3;
+        } else if (b.kind == B200_BINNER_ORDINAL || b.kind == B200_BINNER_HASH) {
+            d.ordinal_count = b.ordinal_count;
+            d.min_value = b.min_value;
+            shape = (unsigned long long)b.ordinal_count + (b.allow_other ? 3 : 2);
+            if (b.kind == B200_BINNER_HASH) {
+                if (!b.set) {
+                    set_error("b200_bin: binner %d: hash binner without a set", i);
+                    return B200_ERR_INVALID;
+                }
+                d.byteswap = 0;
+                B200_CHECK(set_fill_binner(const_cast<b200_set *>(b.set), d));
+            } else {
+                d.byteswap = b.byteswap != 0; // the ordinal FlipEndian quirk flips the int64 difference, any itemsize
+            }
+        } else {
+            set_error("b200_bin: binner %d: unknown kind %d", i, b.kind);
+            return B200_ERR_INVALID;
+        }
+        cells *= shape;
+    }
+    for (int k = 0; k < naggs; k++) {
+        if (!aggs[k].agg) {
+            set_error("b200_bin: aggregator %d is null", k);
+            return B200_ERR_INVALID;
+        }
+        if (aggs[k].agg->cells != cells) {
+            set_error("b200_bin: aggregator %d has %llu cells, the binners span %llu", k, (unsigned long long)aggs[k].agg->cells, cells);
+            return B200_ERR_INVALID;
+        }
+        if (!aggs[k].data && aggs[k].agg->op != B200_AGG_COUNT) {
+            set_error("data not set"); // src/agg_sum.cpp:101-103, src/agg_minmax.cpp:50-52
+            return B200_ERR_NODATA;
+        }
+    }
+
+    Slot *sl = ctx->slots[slot];
+    std::lock_guard<std::mutex> guard(sl->mu);
+    cudaStream_t st = sl->stream;
+
+    // stage host columns (each distinct pointer once)
+    Stager stg{ctx, sl, memspace};
+    for (int i = 0; i < nbinners; i++) {
+        stg.plan(binners[i].data, (size_t)nrows * db[i].isz);
+        if (binners[i].mask)
+            stg.plan(binners[i].mask, (size_t)nrows);
+    }
+    for (int k = 0; k < naggs; k++) {
+        const b200_agg *a = aggs[k].agg;
+        if (aggs[k].data)
+            stg.plan(aggs[k].data, (size_t)nrows * dtype_size(a->dtype));
+        if (aggs[k].order)
+            stg.plan(aggs[k].order, (size_t)nrows * dtype_size(a->dtype2));
+        if (aggs[k].mask) {
+            const bool first = a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST;
+            stg.plan(aggs[k].mask, first ? (size_t)std::min<int64_t>(nrows, 1024) : (size_t)nrows);
+        }
+    }
+    B200_CHECK(stg.commit());
+    bool vec = true;
+    auto chk = [&](const void *p) {
+        if (p && (reinterpret_cast<uintptr_t>(p) & 15))
+            vec = false;
+    };
+    for (int i = 0; i < nbinners; i++) {
+        db[i].data = stg.dev(binners[i].data);
+        db[i].mask = static_cast<const uint8_t *>(stg.dev(binners[i].mask));
+        chk(db[i].data);
+        chk(db[i].mask);
+    }
+
+    // split the aggregators: count/sum/min/max fuse into launches of <= B200_MAX_AGGS; first/last run their two passes each
+    BinParams p;
+    memset(&p, 0, sizeof p);
+    p.nb = nbinners;
+    p.nrows = nrows;
+    p.cells = cells;
+    memcpy(p.b, db, sizeof(DevBinner) * nbinners);
+    auto flush = [&]() -> int {
+        if (!p.na)
+            return B200_OK;
+        bool v = vec;
+        for (int k = 0; k < p.na; k++) {
+            if (p.a[k].data && (reinterpret_cast<uintptr_t>(p.a[k].data) & 15))
+                v = false;
+            if (p.a[k].mask && (reinterpret_cast<uintptr_t>(p.a[k].mask) & 15))
+                v = false;
+        }
+        // privatise in shared memory when one copy of every grid fits comfortably (several copies for tiny grids)
+        size_t copy = 0;
+        for (int k = 0; k < p.na; k++) {
+            p.a[k].smem_cell = p.a[k].op == B200_AGG_COUNT ? 4 : dtype_size(p.a[k].cell_dtype);
+            copy = align_up(copy, 16);
+            p.a[k].smem_off = (int)copy;
+            copy += (size_t)cells * p.a[k].smem_cell;
+        }
+        copy = align_up(copy, 16);
+        const size_t budget = 96 * 1024;
+        p.smem_copies = 0;
+        p.smem_copy_bytes = (int)copy;
+        if (copy <= budget && nrows >= 4096) {
+            int copies = (int)std::min<size_t>(8, (32 * 1024) / copy);
+            p.smem_copies = copies < 1 ? 1 : copies;
+        }
+        int rc = launch_binby(ctx, st, p, v);
+        p.na = 0;
+        return rc;
+    };
+    for (int k = 0; k < naggs; k++) {
+        b200_agg *a = aggs[k].agg;
+        if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST) {
+            FirstParams fp;
+            memset(&fp, 0, sizeof fp);
+            fp.nb = nbinners;
+            fp.nrows = nrows;
+            fp.row_offset = row_offset;
+            memcpy(fp.b, db, sizeof(DevBinner) * nbinners);
+            fp.dtype = a->dtype;
+            fp.isz = dtype_size(a->dtype);
+            fp.dtype2 = a->dtype2;
+            fp.isz2 = dtype_size(a->dtype2);
+            fp.byteswap = a->byteswap;
+            fp.invert = a->op == B200_AGG_LAST;
+            fp.data = stg.dev(aggs[k].data);
+            fp.order = stg.dev(aggs[k].order);
+            fp.mask = static_cast<const uint8_t *>(stg.dev(aggs[k].mask));
+            fp.grid = a->grid;
+            fp.order_grid = a->order;
+            fp.state = static_cast<unsigned long long *>(a->state);
+            fp.cell_masked = a->cell_masked;
+            bool v = vec && !(reinterpret_cast<uintptr_t>(fp.data) & 15) && !(reinterpret_cast<uintptr_t>(fp.order) & 15);
+            // select+deposit of one aggregator must not interleave with another slot's pair on the same grid
+            B200_CUDA(cudaDeviceSynchronize());
+            B200_CHECK(launch_first(ctx, st, fp, v));
+            B200_CUDA(cudaStreamSynchronize(st));
+            continue;
+        }
+        DevAgg &d = p.a[p.na++];
+        memset(&d, 0, sizeof d);
+        d.op = a->op;
+        d.dtype = a->dtype;
+        d.isz = dtype_size(a->dtype);
+        d.byteswap = a->byteswap && d.isz > 1;
+        d.cell_dtype = a->cell_dtype;
+        d.moment = a->moment;
+        d.init_bits = agg_init_bits(a->op, a->cell_dtype);
+        d.data = stg.dev(aggs[k].data);
+        d.mask = static_cast<const uint8_t *>(stg.dev(aggs[k].mask));
+        d.grid = a->grid;
+        if (p.na == B200_MAX_AGGS)
+            B200_CHECK(flush());
+    }
+    B200_CHECK(flush());
+
+    if (memspace == B200_MEM_HOST && !(flags & B200_FLAG_ASYNC_HOST)) {
+        // the caller's buffers are only valid during the call (vaex/cpu.py:708-710).  Callers that keep them alive pass
+        // B200_FLAG_ASYNC_HOST and overlap the next chunk's H2D copy (another slot) with this slot's kernel.
+        B200_CUDA(cudaStreamSynchronize(st));
+    }
+    return B200_OK;
+}
+
+// ---- limits pre-pass -------------------------------------------------------------------------------
+} // extern "C"
+
+namespace b200 {
+namespace {
+__global__ void __launch_bounds__(256) k_minmax(int dtype, int isz, int byteswap, const void *data, const uint8_t *mask, long long nrows, double *out) {
+    double lo = INFINITY, hi = -INFINITY;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += (long long)gridDim.x * blockDim.x) {
+        uint64_t raw;
+        switch (isz) {
+        case 8: raw = __ldcs(static_cast<const unsigned long long *>(data) + i); break;
+        case 4: raw = __ldcs(static_cast<const unsigned *>(data) + i); break;
+        case 2: raw = __ldcs(static_cast<const unsigned short *>(data) + i); break;
+        default: raw = __ldcs(static_cast<const unsigned char *>(data) + i); break;
+        }
+        if (byteswap)
+            raw = bswap(raw, isz);
+        if (mask && mask[i] == 1)
+            continue;
+        double v = raw_to_double(dtype, raw);
+        if (v != v)
+            continue;
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+    for (int o = 16; o; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    __shared__ double slo[8], shi[8];
+    if ((threadIdx.x & 31) == 0) {
+        slo[threadIdx.x >> 5] = lo;
+        shi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) {
+            lo = fmin(lo, slo[w]);
+            hi = fmax(hi, shi[w]);
+        }
+        atomic_min_f64(out, lo);
+        atomic_max_f64(out + 1, hi);
+    }
+}
+} // namespace
+} // namespace b200
+
+extern "C" int b200_minmax(b200_ctx *ctx, int slot, int dtype, int byteswap, const void *data, const uint8_t *mask, int64_t nrows, int memspace,
+                           double *out) {
+    if (!ctx || slot < 0 || slot >= ctx->nslots || dtype < 0 || dtype >= B200_NDTYPE || !out || (nrows && !data)) {
+        set_error("b200_minmax: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(ctx->device));
+    Slot *sl = ctx->slots[slot];
+    std::lock_guard<std::mutex> guard(sl->mu);
+    Stager stg{ctx, sl, memspace};
+    const int isz = dtype_size(dtype);
+    stg.plan(data, (size_t)nrows * isz);
+    if (mask)
+        stg.plan(mask, (size_t)nrows);
+    B200_CHECK(stg.commit());
+    double init[2] = {INFINITY, -INFINITY};
+    double *d = static_cast<double *>(sl->dscratch);
+    B200_CUDA(cudaMemcpyAsync(d, init, sizeof init, cudaMemcpyHostToDevice, sl->stream));
+    if (nrows) {
+        long long want = (nrows + 255) / 256;
+        int blocks = (int)std::min<long long>(want, (long long)ctx->sm_count * 8);
+        k_minmax<<<blocks, 256, 0, sl->stream>>>(dtype, isz, byteswap && isz > 1, stg.dev(data), static_cast<const uint8_t *>(stg.dev(mask)), nrows, d);
+        B200_CUDA(cudaGetLastError());
+    }
+    B200_CUDA(cudaMemcpyAsync(out, d, sizeof init, cudaMemcpyDeviceToHost, sl->stream));
+    B200_CUDA(cudaStreamSynchronize(sl->stream));
+    return B200_OK;
+}

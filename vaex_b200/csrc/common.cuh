@@ -1,0 +1,128 @@
+// common.cuh — shared device/host helpers for libb200agg (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200agg.h"
+
+namespace b200 {
+
+// ---- error plumbing ----------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define B200_CUDA(expr)                                                                                                        \
+    do {                                                                                                                       \
+        cudaError_t e__ = (expr);                                                                                              \
+        if (e__ != cudaSuccess)                                                                                                \
+            return ::b200::cuda_fail(e__, #expr, __FILE__, __LINE__);                                                          \
+    } while (0)
+
+#define B200_CHECK(expr)                                                                                                       \
+    do {                                                                                                                       \
+        int rc__ = (expr);                                                                                                     \
+        if (rc__ != B200_OK)                                                                                                   \
+            return rc__;                                                                                                       \
+    } while (0)
+
+// ---- dtype tables ------------------------------------------------------------------------------
+__host__ __device__ inline int dtype_size(int dt) {
+    switch (dt) {
+    case B200_F64:
+    case B200_I64:
+    case B200_U64: return 8;
+    case B200_F32:
+    case B200_I32:
+    case B200_U32: return 4;
+    case B200_I16:
+    case B200_U16: return 2;
+    default: return 1;
+    }
+}
+__host__ __device__ inline bool dtype_is_float(int dt) { return dt == B200_F64 || dt == B200_F32; }
+__host__ __device__ inline bool dtype_is_signed(int dt) { return dt == B200_I64 || dt == B200_I32 || dt == B200_I16 || dt == B200_I8; }
+// upcast<T> of the reference (src/agg_sum.cpp:6-62): bool counts as signed
+__host__ __device__ inline int dtype_upcast(int dt) {
+    if (dtype_is_float(dt))
+        return B200_F64;
+    if (dtype_is_signed(dt) || dt == B200_BOOL)
+        return B200_I64;
+    return B200_U64;
+}
+// device cell type for min/max grids: 8/16-bit integers are held as 32-bit (no narrow atomics); widened back on read
+__host__ __device__ inline int dtype_minmax_cell(int dt) {
+    switch (dt) {
+    case B200_I16:
+    case B200_I8: return B200_I32;
+    case B200_U16:
+    case B200_U8:
+    case B200_BOOL: return B200_U32;
+    default: return dt;
+    }
+}
+
+// ---- device-side context objects ---------------------------------------------------------------
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t h2d_done = nullptr;
+    void *stage = nullptr; // device staging arena for host chunks
+    size_t stage_cap = 0;
+    void *pinned = nullptr; // small pinned scratch (results of reductions)
+    void *dscratch = nullptr;
+    std::mutex mu;
+};
+
+} // namespace b200
+
+struct b200_ctx {
+    int device = 0;
+    int nslots = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    std::vector<b200::Slot *> slots;
+};
+
+struct b200_agg {
+    b200_ctx *ctx = nullptr;
+    int op = 0, dtype = 0, dtype2 = 0, byteswap = 0;
+    uint32_t moment = 0;
+    uint64_t cells = 0;
+    int cell_dtype = 0;     // device cell type of `grid`
+    void *grid = nullptr;   // cells * dtype_size(cell_dtype)
+    void *state = nullptr;  // FIRST/LAST: cells * 16 B {u64 order key, u64 global row}
+    void *order = nullptr;  // FIRST/LAST: cells * dtype_size(dtype2) raw order values
+    uint8_t *cell_masked = nullptr; // FIRST/LAST
+};
+
+namespace b200 {
+
+// staging: make `n` bytes starting at host/device pointer available on the device for this slot
+struct Stager {
+    b200_ctx *ctx;
+    Slot *slot;
+    int memspace;
+    size_t used = 0;
+    struct Entry {
+        const void *host;
+        size_t bytes;
+        void *dev;
+    };
+    std::vector<Entry> entries;
+    size_t need = 0;
+    // two-phase: plan() every column, then commit() allocates once and issues the copies
+    void plan(const void *p, size_t bytes);
+    int commit();
+    const void *dev(const void *p) const;
+};
+
+int slot_reserve(b200_ctx *ctx, Slot *s, size_t bytes);
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+} // namespace b200

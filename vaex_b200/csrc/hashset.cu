@@ -1,0 +1,748 @@
+// hashset.cu — device ordered_set: the reference's hash-map ordinal encoder
+// (src/hash_primitives.hpp:437-725 ordered_set on hash_base :41-330, hash functors src/hash.hpp:40-152).
+//
+// Reference semantics reproduced (for the sequential, chunks-in-order run of the reference):
+//   * a key's shard is hash<T>(key) % nmaps; its shard-local ordinal is its insertion rank in that shard, i.e.
+//     the rank of its FIRST occurrence in (update call, row) order (_update :98-295 buckets rows in order and
+//     flushes bucket by bucket; add_new :471-479 assigns map.size()).
+//   * NaN / null live in shard 0 and take the next shard-0 ordinal at the END of the update call that first
+//     sees them (:264-287; null before NaN when use_offsets, NaN before null otherwise; add_nan/add_null :454-468).
+//   * global ordinal = shard-local ordinal + offsets[shard] (src/hash.hpp:337-353).
+// Device design: one open-addressing table {key, first-occurrence tag} filled with atomicCAS + atomicMin
+// (tag = call_seq << 40 | row).  Ordinals are materialised lazily: compact -> bitonic sort by (shard, tag) ->
+// position in the sorted list IS the global ordinal -> build a {key, ordinal} probe table (one 16-byte sector
+// per probe) used by map_ordinal / isin and by the fused B200_BINNER_HASH binner.
+#include <algorithm>
+
+#include "binby.cuh"
+#include "device_utils.cuh"
+
+struct b200_set {
+    b200_ctx *ctx = nullptr;
+    int dtype = 0, nmaps = 1;
+    int64_t limit = -1;
+    b200::SetSlot *table = nullptr; // insert table: first = tag
+    uint64_t cap = 0;
+    unsigned long long *d_ctr = nullptr; // see CTR_*
+    int64_t seq = 0;
+    bool dirty = true;
+    // finalized view
+    b200::SetSlot *probe = nullptr; // first = global ordinal
+    uint64_t probe_cap = 0;
+    long long *d_offsets = nullptr; // nmaps
+    std::vector<uint64_t> h_keys;   // canonical patterns in ordinal order (special slots hold 0)
+    std::vector<int64_t> h_offsets;
+    int64_t n_keys = 0, nan_count = 0, null_count = 0;
+    int64_t nan_value = 0x7fffffff, null_value = 0x7fffffff; // src/hash_primitives.hpp:447
+    int64_t sentinel_ordinal = -1;
+    std::mutex mu;
+};
+
+namespace b200 {
+
+enum { CTR_COUNT = 0, CTR_OVERFLOW, CTR_NAN_COUNT, CTR_NULL_COUNT, CTR_NAN_TAG, CTR_NULL_TAG, CTR_SENTINEL_TAG, CTR_CURSOR, CTR_N };
+
+namespace {
+
+constexpr unsigned long long kTagLowMask = (1ULL << 40) - 1;
+
+struct Entry {
+    unsigned long long hi;  // shard
+    unsigned long long tag; // first occurrence
+    unsigned long long key;
+};
+
+__device__ __forceinline__ uint64_t load_raw1(const void *data, int isz, long long i) {
+    switch (isz) {
+    case 8: return __ldcs(static_cast<const unsigned long long *>(data) + i);
+    case 4: return __ldcs(static_cast<const unsigned *>(data) + i);
+    case 2: return __ldcs(static_cast<const unsigned short *>(data) + i);
+    default: return __ldcs(static_cast<const unsigned char *>(data) + i);
+    }
+}
+
+// insert (or touch) one key; returns false when the table is too full
+__device__ __forceinline__ bool table_insert(SetSlot *table, unsigned long long mask, unsigned long long *ctr, unsigned long long max_fill,
+                                             unsigned long long canon, unsigned long long tag) {
+    unsigned long long h = hash64(canon) & mask;
+    while (true) {
+        unsigned long long k = table[h].key;
+        if (k == canon) {
+            if (tag < *reinterpret_cast<volatile unsigned long long *>(&table[h].first))
+                atomicMin(&table[h].first, tag);
+            return true;
+        }
+        if (k == SET_EMPTY) {
+            // reserve a unit of capacity BEFORE claiming the slot, so the table can never fill past max_fill
+            // (an over-full open-addressing table would make the probe loops spin forever)
+            if (*reinterpret_cast<volatile unsigned long long *>(ctr + CTR_COUNT) >= max_fill)
+                return false;
+            if (atomicAdd(ctr + CTR_COUNT, 1ull) >= max_fill) {
+                atomicAdd(ctr + CTR_COUNT, ~0ull); // -1
+                return false;
+            }
+            unsigned long long old = atomicCAS(&table[h].key, SET_EMPTY, canon);
+            if (old == SET_EMPTY) {
+                atomicMin(&table[h].first, tag);
+                return true;
+            }
+            atomicAdd(ctr + CTR_COUNT, ~0ull); // lost the race for this slot: give the reservation back
+            if (old == canon) {
+                atomicMin(&table[h].first, tag);
+                return true;
+            }
+        }
+        h = (h + 1) & mask;
+    }
+}
+
+// hash_base::_update (src/hash_primitives.hpp:98-295).  from_keys: ordered_set::create (:486-537) where row i IS the ordinal.
+__global__ void __launch_bounds__(256) k_set_insert(SetSlot *table, unsigned long long mask, unsigned long long *ctr, unsigned long long max_fill, int dtype,
+                                                    int isz, const void *keys, const uint8_t *masks, long long row0, long long nrows,
+                                                    unsigned long long tag_base, int skip_keys, long long from_keys_null_index, int from_keys,
+                                                    unsigned long long nan_low, unsigned long long null_low) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = row0 + i;
+        uint64_t raw = load_raw1(keys, isz, row);
+        bool isnull = from_keys ? (row == from_keys_null_index) : (masks && masks[row]);
+        if (isnull) {
+            atomicAdd(ctr + CTR_NULL_COUNT, 1ull);
+            atomicMin(ctr + CTR_NULL_TAG, from_keys ? (unsigned long long)row : (tag_base | null_low));
+            continue;
+        }
+        if (raw_isnan(dtype, raw)) {
+            atomicAdd(ctr + CTR_NAN_COUNT, 1ull);
+            atomicMin(ctr + CTR_NAN_TAG, from_keys ? (unsigned long long)row : (tag_base | nan_low));
+            continue;
+        }
+        if (skip_keys)
+            continue;
+        unsigned long long canon = key_canon(dtype, raw);
+        unsigned long long tag = tag_base | (unsigned long long)row;
+        if (canon == SET_EMPTY) {
+            atomicMin(ctr + CTR_SENTINEL_TAG, tag);
+            continue;
+        }
+        if (!table_insert(table, mask, ctr, max_fill, canon, tag))
+            ctr[CTR_OVERFLOW] = 1ull;
+    }
+}
+
+__global__ void k_set_init(SetSlot *table, unsigned long long cap) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (unsigned long long)gridDim.x * blockDim.x) {
+        table[i].key = SET_EMPTY;
+        table[i].first = 0xFFFFFFFFFFFFFFFFULL;
+    }
+}
+
+__global__ void k_set_rehash(const SetSlot *old, unsigned long long old_cap, SetSlot *table, unsigned long long mask) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < old_cap; i += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long k = old[i].key;
+        if (k == SET_EMPTY)
+            continue;
+        unsigned long long h = hash64(k) & mask;
+        while (atomicCAS(&table[h].key, SET_EMPTY, k) != SET_EMPTY)
+            h = (h + 1) & mask;
+        table[h].first = old[i].first;
+    }
+}
+
+__global__ void k_set_compact(const SetSlot *table, unsigned long long cap, unsigned long long *ctr, Entry *out, int dtype, int nmaps) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long k = table[i].key;
+        if (k == SET_EMPTY)
+            continue;
+        unsigned long long pos = atomicAdd(ctr + CTR_CURSOR, 1ull);
+        out[pos].hi = key_hash(dtype, k) % (unsigned long long)nmaps;
+        out[pos].tag = table[i].first;
+        out[pos].key = k;
+    }
+}
+
+__global__ void k_fill_entries(Entry *e, unsigned long long from, unsigned long long to) {
+    for (unsigned long long i = from + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < to; i += (unsigned long long)gridDim.x * blockDim.x) {
+        e[i].hi = 0xFFFFFFFFFFFFFFFFULL;
+        e[i].tag = 0xFFFFFFFFFFFFFFFFULL;
+        e[i].key = 0;
+    }
+}
+
+// one compare-exchange stage of a bitonic sort on (hi, tag)
+__global__ void k_bitonic(Entry *e, unsigned long long n, unsigned long long j, unsigned long long k) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long l = i ^ j;
+        if (l > i) {
+            Entry a = e[i], b = e[l];
+            const bool a_gt_b = a.hi > b.hi || (a.hi == b.hi && a.tag > b.tag);
+            const bool a_lt_b = a.hi < b.hi || (a.hi == b.hi && a.tag < b.tag);
+            const bool up = (i & k) == 0;
+            if (up ? a_gt_b : a_lt_b) {
+                e[i] = b;
+                e[l] = a;
+            }
+        }
+    }
+}
+
+__global__ void k_probe_build(SetSlot *probe, unsigned long long mask, const Entry *e, unsigned long long n, unsigned long long skip0, unsigned long long skip1,
+                              unsigned long long skip2) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        if (i == skip0 || i == skip1 || i == skip2)
+            continue; // NaN / null / sentinel-key positions
+        unsigned long long k = e[i].key;
+        unsigned long long h = hash64(k) & mask;
+        while (atomicCAS(&probe[h].key, SET_EMPTY, k) != SET_EMPTY)
+            h = (h + 1) & mask;
+        probe[h].first = i;
+    }
+}
+
+__device__ __forceinline__ long long probe_lookup(const SetSlot *probe, unsigned long long mask, long long sentinel_ordinal, unsigned long long canon) {
+    if (canon == SET_EMPTY)
+        return sentinel_ordinal;
+    unsigned long long h = hash64(canon) & mask;
+    while (true) {
+        const ulonglong2 s = __ldg(reinterpret_cast<const ulonglong2 *>(probe + h));
+        if (s.x == canon)
+            return (long long)s.y;
+        if (s.x == SET_EMPTY)
+            return -1;
+        h = (h + 1) & mask;
+    }
+}
+
+// ordered_set::_map_ordinal (src/hash_primitives.hpp:624-691).  out_isz selects int8/16/32/64; out_isz == 0: isin (uint8)
+__global__ void __launch_bounds__(256) k_set_map(const SetSlot *probe, unsigned long long mask, long long sentinel_ordinal, long long nan_ordinal, int dtype,
+                                                 int isz, const void *keys, long long nrows, void *out, int out_isz) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += (long long)gridDim.x * blockDim.x) {
+        uint64_t raw = load_raw1(keys, isz, i);
+        long long v = raw_isnan(dtype, raw) ? nan_ordinal : probe_lookup(probe, mask, sentinel_ordinal, key_canon(dtype, raw));
+        switch (out_isz) {
+        case 0: static_cast<unsigned char *>(out)[i] = v >= 0; break;
+        case 1: static_cast<signed char *>(out)[i] = (signed char)v; break;
+        case 2: static_cast<short *>(out)[i] = (short)v; break;
+        case 4: static_cast<int *>(out)[i] = (int)v; break;
+        default: static_cast<long long *>(out)[i] = v; break;
+        }
+    }
+}
+
+// update(..., return_values=True): per row the shard-local ordinal and the shard (src/hash_primitives.hpp:139-176)
+__global__ void __launch_bounds__(256) k_set_values(const SetSlot *probe, unsigned long long mask, long long sentinel_ordinal, long long nan_ordinal,
+                                                    long long null_ordinal, int dtype, int isz, int nmaps, const long long *offsets, const void *keys,
+                                                    const uint8_t *masks, long long nrows, long long *out_values, short *out_map) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += (long long)gridDim.x * blockDim.x) {
+        uint64_t raw = load_raw1(keys, isz, i);
+        if (masks && masks[i]) {
+            out_values[i] = null_ordinal;
+            out_map[i] = 0;
+        } else if (raw_isnan(dtype, raw)) {
+            out_values[i] = nan_ordinal;
+            out_map[i] = 0;
+        } else {
+            unsigned long long canon = key_canon(dtype, raw);
+            int shard = (int)(key_hash(dtype, canon) % (unsigned long long)nmaps);
+            long long g = probe_lookup(probe, mask, sentinel_ordinal, canon);
+            out_values[i] = g - offsets[shard];
+            out_map[i] = (short)shard;
+        }
+    }
+}
+
+inline int nblocks(unsigned long long n, int threads = 256) {
+    unsigned long long b = (n + threads - 1) / threads;
+    return (int)(b < 148ull * 8 ? (b ? b : 1) : 148ull * 8);
+}
+
+int set_alloc_table(b200_set *s, uint64_t cap, cudaStream_t st) {
+    B200_CUDA(cudaMalloc(&s->table, cap * sizeof(SetSlot)));
+    s->cap = cap;
+    k_set_init<<<nblocks(cap), 256, 0, st>>>(s->table, cap);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
+int set_grow(b200_set *s, cudaStream_t st) {
+    SetSlot *old = s->table;
+    uint64_t old_cap = s->cap;
+    B200_CHECK(set_alloc_table(s, old_cap * 4, st));
+    k_set_rehash<<<nblocks(old_cap), 256, 0, st>>>(old, old_cap, s->table, s->cap - 1);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaStreamSynchronize(st));
+    B200_CUDA(cudaFree(old));
+    return B200_OK;
+}
+
+int read_ctr(b200_set *s, cudaStream_t st, unsigned long long *h) {
+    B200_CUDA(cudaMemcpyAsync(h, s->d_ctr, sizeof(unsigned long long) * CTR_N, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+// lazily materialise ordinals; caller holds s->mu
+int set_finalize(b200_set *s) {
+    if (!s->dirty)
+        return B200_OK;
+    B200_CUDA(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->slots[0]->stream;
+    unsigned long long h[CTR_N];
+    unsigned long long zero = 0;
+    B200_CUDA(cudaMemcpyAsync(s->d_ctr + CTR_CURSOR, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
+    B200_CHECK(read_ctr(s, st, h));
+    const bool has_nan = h[CTR_NAN_COUNT] > 0, has_null = h[CTR_NULL_COUNT] > 0, has_sent = h[CTR_SENTINEL_TAG] != 0xFFFFFFFFFFFFFFFFULL;
+    const unsigned long long n_table = h[CTR_COUNT];
+    const unsigned long long E = n_table + has_nan + has_null + has_sent;
+    unsigned long long P = 1;
+    while (P < E)
+        P <<= 1;
+    Entry *d_e = nullptr;
+    B200_CUDA(cudaMalloc(&d_e, sizeof(Entry) * (P ? P : 1)));
+    if (n_table)
+        k_set_compact<<<nblocks(s->cap), 256, 0, st>>>(s->table, s->cap, s->d_ctr, d_e, s->dtype, s->nmaps);
+    Entry extra[3];
+    int ne = 0;
+    if (has_sent)
+        extra[ne++] = Entry{key_hash(s->dtype, SET_EMPTY) % (unsigned long long)s->nmaps, h[CTR_SENTINEL_TAG], SET_EMPTY};
+    if (has_nan)
+        extra[ne++] = Entry{0, h[CTR_NAN_TAG], 0};
+    if (has_null)
+        extra[ne++] = Entry{0, h[CTR_NULL_TAG], 0};
+    if (ne)
+        B200_CUDA(cudaMemcpyAsync(d_e + n_table, extra, sizeof(Entry) * ne, cudaMemcpyHostToDevice, st));
+    if (P > E)
+        k_fill_entries<<<nblocks(P - E), 256, 0, st>>>(d_e, E, P);
+    for (unsigned long long k = 2; k <= P; k <<= 1)
+        for (unsigned long long j = k >> 1; j > 0; j >>= 1)
+            k_bitonic<<<nblocks(P), 256, 0, st>>>(d_e, P, j, k);
+    B200_CUDA(cudaGetLastError());
+    std::vector<Entry> he(E);
+    if (E)
+        B200_CUDA(cudaMemcpyAsync(he.data(), d_e, sizeof(Entry) * E, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+
+    s->h_keys.assign(E, 0);
+    s->h_offsets.assign(s->nmaps, 0);
+    s->nan_count = (int64_t)h[CTR_NAN_COUNT];
+    s->null_count = (int64_t)h[CTR_NULL_COUNT];
+    s->nan_value = s->null_value = 0x7fffffff;
+    s->sentinel_ordinal = -1;
+    s->n_keys = (int64_t)(n_table + has_sent);
+    std::vector<int64_t> per_shard(s->nmaps, 0);
+    // NaN and null carry distinct tags unless created by from_keys with equal rows (impossible: distinct rows)
+    for (unsigned long long i = 0; i < E; i++) {
+        const Entry &e = he[i];
+        per_shard[e.hi]++;
+        if (has_nan && e.hi == 0 && e.tag == h[CTR_NAN_TAG] && s->nan_value == 0x7fffffff && e.key == 0 && !(has_null && e.tag == h[CTR_NULL_TAG])) {
+            s->nan_value = (int64_t)i;
+        } else if (has_null && e.hi == 0 && e.tag == h[CTR_NULL_TAG] && s->null_value == 0x7fffffff && e.key == 0) {
+            s->null_value = (int64_t)i;
+        } else {
+            s->h_keys[i] = e.key;
+            if (e.key == SET_EMPTY)
+                s->sentinel_ordinal = (int64_t)i;
+        }
+    }
+    int64_t off = 0;
+    for (int m = 0; m < s->nmaps; m++) {
+        s->h_offsets[m] = off;
+        off += per_shard[m];
+    }
+    // probe table
+    if (s->probe)
+        B200_CUDA(cudaFree(s->probe));
+    uint64_t pc = 16;
+    while (pc < 2 * (n_table + 1))
+        pc <<= 1;
+    B200_CUDA(cudaMalloc(&s->probe, pc * sizeof(SetSlot)));
+    s->probe_cap = pc;
+    k_set_init<<<nblocks(pc), 256, 0, st>>>(s->probe, pc);
+    if (E)
+        k_probe_build<<<nblocks(E), 256, 0, st>>>(s->probe, pc - 1, d_e, E, has_nan ? (unsigned long long)s->nan_value : ~0ull,
+                                                  has_null ? (unsigned long long)s->null_value : ~0ull,
+                                                  has_sent ? (unsigned long long)s->sentinel_ordinal : ~0ull);
+    if (!s->d_offsets)
+        B200_CUDA(cudaMalloc(&s->d_offsets, sizeof(long long) * s->nmaps));
+    B200_CUDA(cudaMemcpyAsync(s->d_offsets, s->h_offsets.data(), sizeof(long long) * s->nmaps, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaStreamSynchronize(st));
+    B200_CUDA(cudaFree(d_e));
+    s->dirty = false;
+    return B200_OK;
+}
+
+int64_t set_count_locked(b200_set *s) { return s->n_keys + (s->nan_count > 0) + (s->null_count > 0); }
+
+// insert rows [0, nrows) of device arrays; caller holds s->mu
+int set_insert_device(b200_set *s, cudaStream_t st, const void *d_keys, const uint8_t *d_masks, int64_t nrows, bool use_offsets, bool from_keys,
+                      int64_t from_keys_null_index) {
+    unsigned long long h[CTR_N];
+    int skip_keys = 0;
+    if (s->limit >= 0) { // hash_primitives.hpp:237-249: a full set skips the whole flush of this call
+        B200_CHECK(set_finalize(s));
+        if (set_count_locked(s) >= s->limit)
+            skip_keys = 1;
+    }
+    const unsigned long long tag_base = from_keys ? 0ull : ((unsigned long long)s->seq << 40);
+    s->seq++;
+    const unsigned long long first_low = kTagLowMask - 1, second_low = kTagLowMask;
+    const unsigned long long null_low = use_offsets ? first_low : second_low;
+    const unsigned long long nan_low = use_offsets ? second_low : first_low;
+    const int isz = dtype_size(s->dtype);
+    const int64_t sub = 1ll << 26;
+    for (int64_t row0 = 0; row0 < nrows;) {
+        int64_t n = std::min<int64_t>(sub, nrows - row0);
+        k_set_insert<<<nblocks((unsigned long long)n), 256, 0, st>>>(s->table, s->cap - 1, s->d_ctr, s->cap / 2, s->dtype, isz, d_keys, d_masks, row0, n,
+                                                                     tag_base, skip_keys, from_keys_null_index, from_keys ? 1 : 0, nan_low, null_low);
+        B200_CUDA(cudaGetLastError());
+        B200_CHECK(read_ctr(s, st, h));
+        if (h[CTR_OVERFLOW]) {
+            unsigned long long zero = 0;
+            B200_CUDA(cudaMemcpyAsync(s->d_ctr + CTR_OVERFLOW, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
+            B200_CHECK(set_grow(s, st));
+            continue; // redo this range: inserts are idempotent (CAS claim + atomicMin of the tag)
+        }
+        row0 += n;
+    }
+    s->dirty = true;
+    return B200_OK;
+}
+
+} // namespace
+
+// used by the C-ABI layer for B200_BINNER_HASH
+int set_fill_binner(b200_set *s, DevBinner &b) {
+    std::lock_guard<std::mutex> g(s->mu);
+    B200_CHECK(set_finalize(s));
+    b.table = s->probe;
+    b.table_mask = s->probe_cap - 1;
+    b.nan_ordinal = s->nan_count > 0 ? s->nan_value : -1;
+    b.null_ordinal = s->null_count > 0 ? s->null_value : -1;
+    b.sentinel_ordinal = s->sentinel_ordinal;
+    return B200_OK;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_set_create(b200_ctx *ctx, int dtype, int nmaps, int64_t limit, b200_set **out) {
+    if (!ctx || !out || dtype < 0 || dtype >= B200_NDTYPE || nmaps < 1 || nmaps > 32767) {
+        set_error("b200_set_create: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(ctx->device));
+    b200_set *s = new b200_set;
+    s->ctx = ctx;
+    s->dtype = dtype;
+    s->nmaps = nmaps;
+    s->limit = limit;
+    cudaStream_t st = ctx->slots[0]->stream;
+    int rc = set_alloc_table(s, 1ull << 12, st);
+    if (rc) {
+        delete s;
+        return rc;
+    }
+    B200_CUDA(cudaMalloc(&s->d_ctr, sizeof(unsigned long long) * CTR_N));
+    unsigned long long init[CTR_N] = {0, 0, 0, 0, ~0ull, ~0ull, ~0ull, 0};
+    B200_CUDA(cudaMemcpyAsync(s->d_ctr, init, sizeof init, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    *out = s;
+    return B200_OK;
+}
+
+int b200_set_destroy(b200_set *s) {
+    if (!s)
+        return B200_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaFree(s->table);
+    cudaFree(s->probe);
+    cudaFree(s->d_ctr);
+    cudaFree(s->d_offsets);
+    delete s;
+    return B200_OK;
+}
+
+int b200_set_update(b200_set *s, int slot, const void *keys, const uint8_t *masks, int64_t nrows, int64_t start_index, int return_values,
+                    int64_t *out_values, int16_t *out_map_index, int memspace, uint32_t flags) {
+    if (!s || slot < 0 || slot >= s->ctx->nslots || nrows < 0 || (nrows && !keys)) {
+        set_error("b200_set_update: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    if (s->limit >= 0 && return_values) {
+        set_error("Cannot combine limit with return_inverse"); // hash_primitives.hpp:102-104
+        return B200_ERR_STATE;
+    }
+    if (nrows >= (1ll << 40) - 2) {
+        set_error("b200_set_update: more than 2^40 rows in one call");
+        return B200_ERR_UNSUPPORTED;
+    }
+    B200_CUDA(cudaSetDevice(s->ctx->device));
+    Slot *sl = s->ctx->slots[slot];
+    std::lock_guard<std::mutex> g(s->mu);
+    std::lock_guard<std::mutex> gs(sl->mu);
+    Stager stg{s->ctx, sl, memspace};
+    const size_t isz = dtype_size(s->dtype);
+    stg.plan(keys, (size_t)nrows * isz);
+    if (masks)
+        stg.plan(masks, (size_t)nrows);
+    B200_CHECK(stg.commit());
+    const void *d_keys = stg.dev(keys);
+    const uint8_t *d_masks = masks ? static_cast<const uint8_t *>(stg.dev(masks)) : nullptr;
+    const bool use_offsets = return_values || start_index != -1;
+    B200_CHECK(set_insert_device(s, sl->stream, d_keys, d_masks, nrows, use_offsets, false, -1));
+    if (return_values && nrows) {
+        B200_CHECK(set_finalize(s));
+        long long *d_vals = nullptr;
+        short *d_map = nullptr;
+        B200_CUDA(cudaMalloc(&d_vals, sizeof(long long) * nrows));
+        B200_CUDA(cudaMalloc(&d_map, sizeof(short) * nrows));
+        k_set_values<<<nblocks((unsigned long long)nrows), 256, 0, sl->stream>>>(s->probe, s->probe_cap - 1, s->sentinel_ordinal, s->nan_value, s->null_value,
+                                                                               s->dtype, (int)isz, s->nmaps, s->d_offsets, d_keys, d_masks, nrows, d_vals, d_map);
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaMemcpyAsync(out_values, d_vals, sizeof(long long) * nrows, cudaMemcpyDeviceToHost, sl->stream));
+        B200_CUDA(cudaMemcpyAsync(out_map_index, d_map, sizeof(short) * nrows, cudaMemcpyDeviceToHost, sl->stream));
+        B200_CUDA(cudaStreamSynchronize(sl->stream));
+        cudaFree(d_vals);
+        cudaFree(d_map);
+    }
+    (void)flags;
+    return B200_OK;
+}
+
+int b200_set_from_keys(b200_ctx *ctx, int dtype, const void *keys, int64_t nkeys, int64_t null_index, int64_t nan_count, int64_t null_count,
+                       b200_set **out) {
+    b200_set *s = nullptr;
+    B200_CHECK(b200_set_create(ctx, dtype, 1, -1, &s));
+    int rc = B200_OK;
+    {
+        Slot *sl = ctx->slots[0];
+        std::lock_guard<std::mutex> g(s->mu);
+        std::lock_guard<std::mutex> gs(sl->mu);
+        Stager stg{ctx, sl, B200_MEM_HOST};
+        stg.plan(keys, (size_t)nkeys * dtype_size(dtype));
+        rc = stg.commit();
+        if (!rc && nkeys)
+            rc = set_insert_device(s, sl->stream, stg.dev(keys), nullptr, nkeys, true, true, null_index);
+        if (!rc)
+            rc = set_finalize(s);
+        if (!rc) {
+            // ordered_set::create validation (src/hash_primitives.hpp:504-530)
+            const char *msg = nullptr;
+            if (nan_count == 0 && s->nan_count != 0)
+                msg = "NaN found in data, while claiming there should be none";
+            else if (nan_count != 0 && s->nan_count == 0)
+                msg = "no NaN found in data, while claiming there should be";
+            else if (null_count == 0 && s->null_count != 0)
+                msg = "null found in data, while claiming there should be none";
+            else if (null_count != 0 && s->null_count == 0)
+                msg = "no null found in data, while claiming there should be";
+            else if (null_count != 0 && s->null_value != null_index)
+                msg = "null_value does not match expected value";
+            else if (set_count_locked(s) != nkeys)
+                msg = "key array length does not match expected length (duplicate keys)";
+            if (msg) {
+                set_error("%s", msg);
+                rc = B200_ERR_STATE;
+            } else {
+                s->nan_count = nan_count;
+                s->null_count = null_count;
+            }
+        }
+    }
+    if (rc) {
+        b200_set_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return B200_OK;
+}
+
+// ordered_set::merge (src/hash_primitives.hpp:693-720).  The reference appends unseen keys in the other map's
+// hopscotch iteration order (container-internal); here they are appended in the other set's ORDINAL order —
+// a documented, deterministic deviation (merging distinct sets does not occur in the reference's own flow:
+// TaskPartHashmapUniqueCreate.ideal_splits() == 1, vaex/cpu.py:362-364).
+int b200_set_merge(b200_set *s, b200_set *const *others, int nothers) {
+    if (!s) {
+        set_error("b200_set_merge: null set");
+        return B200_ERR_INVALID;
+    }
+    for (int i = 0; i < nothers; i++)
+        if (others[i]->nmaps != s->nmaps || others[i]->dtype != s->dtype) {
+            set_error("cannot merge with an unequal maps");
+            return B200_ERR_STATE;
+        }
+    B200_CUDA(cudaSetDevice(s->ctx->device));
+    for (int i = 0; i < nothers; i++) {
+        b200_set *o = others[i];
+        std::vector<uint64_t> keys;
+        int64_t o_nan, o_null;
+        {
+            std::lock_guard<std::mutex> g(o->mu);
+            B200_CHECK(set_finalize(o));
+            keys.reserve(o->h_keys.size());
+            for (size_t k = 0; k < o->h_keys.size(); k++)
+                if ((int64_t)k != o->nan_value && (int64_t)k != o->null_value)
+                    keys.push_back(o->h_keys[k]);
+            o_nan = o->nan_count;
+            o_null = o->null_count;
+        }
+        Slot *sl = s->ctx->slots[0];
+        std::lock_guard<std::mutex> g(s->mu);
+        std::lock_guard<std::mutex> gs(sl->mu);
+        // feed canonical patterns as a 64-bit column of a same-hash dtype: U64 for hashed types keeps hash64(canon)
+        // identical; identity-hashed small ints also stay identical because key_hash(dtype, canon) == canon there.
+        int saved = s->dtype;
+        Stager stg{s->ctx, sl, B200_MEM_HOST};
+        stg.plan(keys.data(), keys.size() * 8);
+        B200_CHECK(stg.commit());
+        // canonical patterns re-enter through a raw 64-bit view; key_canon(U64) is the identity and the shard hash is
+        // evaluated from s->dtype at finalize, so only the column width differs.
+        s->dtype = B200_U64;
+        int rc = keys.empty() ? B200_OK : set_insert_device(s, sl->stream, stg.dev(keys.data()), nullptr, (int64_t)keys.size(), false, false, -1);
+        s->dtype = saved;
+        B200_CHECK(rc);
+        // nan/null: counts add up; a special first seen through a merge takes the next shard-0 ordinal
+        unsigned long long h[CTR_N];
+        B200_CHECK(read_ctr(s, sl->stream, h));
+        const unsigned long long tag_base = (unsigned long long)(s->seq - (keys.empty() ? 0 : 1)) << 40;
+        if (keys.empty())
+            s->seq++;
+        if (o_nan) {
+            h[CTR_NAN_COUNT] += (unsigned long long)o_nan;
+            if (h[CTR_NAN_TAG] == ~0ull)
+                h[CTR_NAN_TAG] = tag_base | (kTagLowMask - 1);
+        }
+        if (o_null) {
+            h[CTR_NULL_COUNT] += (unsigned long long)o_null;
+            if (h[CTR_NULL_TAG] == ~0ull)
+                h[CTR_NULL_TAG] = tag_base | kTagLowMask;
+        }
+        B200_CUDA(cudaMemcpyAsync(s->d_ctr, h, sizeof h, cudaMemcpyHostToDevice, sl->stream));
+        B200_CUDA(cudaStreamSynchronize(sl->stream));
+        s->dirty = true;
+    }
+    return B200_OK;
+}
+
+#define SET_GETTER(name, expr)                                                                                                 \
+    int64_t b200_set_##name(b200_set *s) {                                                                                     \
+        if (!s)                                                                                                                \
+            return -1;                                                                                                         \
+        std::lock_guard<std::mutex> g(s->mu);                                                                                  \
+        if (set_finalize(s))                                                                                                   \
+            return -1;                                                                                                         \
+        return (expr);                                                                                                         \
+    }
+SET_GETTER(count, set_count_locked(s))
+SET_GETTER(nan_count, s->nan_count)
+SET_GETTER(null_count, s->null_count)
+SET_GETTER(nan_index, s->nan_value)
+SET_GETTER(null_index, s->null_value)
+
+int b200_set_nmaps(const b200_set *s) { return s ? s->nmaps : -1; }
+
+int b200_set_offsets(b200_set *s, int64_t *out) {
+    std::lock_guard<std::mutex> g(s->mu);
+    B200_CHECK(set_finalize(s));
+    for (int m = 0; m < s->nmaps; m++)
+        out[m] = s->h_offsets[m];
+    return B200_OK;
+}
+
+// hash_base::key_array (src/hash_primitives.hpp:302-328): NaN slot holds NaN, null slot holds (T)-1
+int b200_set_key_array(b200_set *s, void *out) {
+    std::lock_guard<std::mutex> g(s->mu);
+    B200_CHECK(set_finalize(s));
+    const int isz = dtype_size(s->dtype);
+    for (size_t i = 0; i < s->h_keys.size(); i++) {
+        uint64_t bits = s->h_keys[i];
+        if (s->nan_count > 0 && (int64_t)i == s->nan_value)
+            bits = s->dtype == B200_F64 ? 0x7ff8000000000000ULL : 0x7fc00000u;
+        if (s->null_count > 0 && (int64_t)i == s->null_value) {
+            if (s->dtype == B200_F64)
+                bits = 0xbff0000000000000ULL; // -1.0
+            else if (s->dtype == B200_F32)
+                bits = 0xbf800000u;
+            else if (s->dtype == B200_BOOL)
+                bits = 1;
+            else
+                bits = ~0ull;
+        }
+        switch (isz) {
+        case 8: static_cast<uint64_t *>(out)[i] = bits; break;
+        case 4: static_cast<uint32_t *>(out)[i] = (uint32_t)bits; break;
+        case 2: static_cast<uint16_t *>(out)[i] = (uint16_t)bits; break;
+        default: static_cast<uint8_t *>(out)[i] = (uint8_t)bits; break;
+        }
+    }
+    return B200_OK;
+}
+
+int b200_set_ordinal_dtype(b200_set *s) {
+    int64_t size = b200_set_count(s);
+    if (size < (1 << 7))
+        return B200_I8;
+    if (size < (1 << 15))
+        return B200_I16;
+    if (size < (1ll << 31))
+        return B200_I32;
+    return B200_I64;
+}
+
+static int set_map_common(b200_set *s, int slot, const void *keys, int64_t nrows, void *out, int out_isz, int memspace) {
+    if (!s || slot < 0 || slot >= s->ctx->nslots || nrows < 0) {
+        set_error("b200_set_map: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    if (!nrows)
+        return B200_OK;
+    B200_CUDA(cudaSetDevice(s->ctx->device));
+    Slot *sl = s->ctx->slots[slot];
+    std::lock_guard<std::mutex> g(s->mu);
+    B200_CHECK(set_finalize(s));
+    std::lock_guard<std::mutex> gs(sl->mu);
+    Stager stg{s->ctx, sl, memspace};
+    const size_t isz = dtype_size(s->dtype);
+    const size_t osz = out_isz ? out_isz : 1;
+    stg.plan(keys, (size_t)nrows * isz);
+    B200_CHECK(stg.commit());
+    void *d_out = out;
+    if (memspace == B200_MEM_HOST)
+        B200_CUDA(cudaMalloc(&d_out, nrows * osz));
+    k_set_map<<<nblocks((unsigned long long)nrows), 256, 0, sl->stream>>>(s->probe, s->probe_cap - 1, s->sentinel_ordinal,
+                                                                        s->nan_count > 0 ? s->nan_value : -1, s->dtype, (int)isz, stg.dev(keys), nrows, d_out,
+                                                                        out_isz);
+    B200_CUDA(cudaGetLastError());
+    if (memspace == B200_MEM_HOST) {
+        B200_CUDA(cudaMemcpyAsync(out, d_out, nrows * osz, cudaMemcpyDeviceToHost, sl->stream));
+        B200_CUDA(cudaStreamSynchronize(sl->stream));
+        cudaFree(d_out);
+    }
+    return B200_OK;
+}
+
+int b200_set_map_ordinal(b200_set *s, int slot, const void *keys, int64_t nrows, void *out, int memspace, uint32_t flags) {
+    (void)flags;
+    int od = b200_set_ordinal_dtype(s);
+    return set_map_common(s, slot, keys, nrows, out, dtype_size(od), memspace);
+}
+
+// ordered_set::isin (src/hash_primitives.hpp:539-565); NaN is "in" iff the set saw a NaN
+int b200_set_isin(b200_set *s, int slot, const void *keys, int64_t nrows, uint8_t *out, int memspace, uint32_t flags) {
+    (void)flags;
+    return set_map_common(s, slot, keys, nrows, out, 0, memspace);
+}
+
+// hash_base::bytes_used (src/hash_primitives.hpp:62-69): sum over maps of size * (sizeof(key) + sizeof(value))
+size_t b200_set_bytes(b200_set *s) {
+    std::lock_guard<std::mutex> g(s->mu);
+    if (set_finalize(s))
+        return 0;
+    return (size_t)s->n_keys * (dtype_size(s->dtype) + 8);
+}
+
+uint64_t b200_hash64(uint64_t x) { return hash64(x); }
+
+} // extern "C"

@@ -1,0 +1,80 @@
+"""Row-sharded multi-GPU driver: one process per GPU, each bins its row range into its own full-size grids, then ONE
+NCCL all-reduce per grid over NVLink (sum for count/sum/moment grids, min/max for min/max grids).
+
+This is the B200 replacement for the reference's only parallel strategy on this path — row-range data parallelism over
+threads with private grids merged at the end (vaex/execution.py:432-455, src/agg_base.hpp:33-48, src/agg_count.cpp:24-41).
+torch is used for plumbing only: `torch.distributed` (NCCL) and zero-copy tensor views of the device grids.
+"""
+import numpy as np
+
+from . import _lib
+
+_TORCH_DTYPE = {"float64": "float64", "float32": "float32", "int64": "int64", "int32": "int32", "uint64": "int64", "uint32": "int32"}
+
+
+class _GridView:
+    """Exposes an aggregator's device grid through __cuda_array_interface__ (no copy, no ownership)."""
+
+    def __init__(self, agg, which=0):
+        ptr, nbytes = agg.device_pointer(which)
+        dt = agg.device_dtype if which == 0 else np.dtype("uint64")
+        # torch has no uint64/uint32 reductions: view them as the signed type of equal width (add is two's complement;
+        # min/max on unsigned grids are handled separately in all_reduce_agg)
+        name = _TORCH_DTYPE[dt.name]
+        self._agg = agg
+        self.signed_view = name != dt.name
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes // dt.itemsize,),
+            "typestr": np.dtype(name).str,
+            "data": (ptr, False),
+            "version": 3,
+            "strides": None,
+        }
+
+
+def grid_tensor(agg, which=0):
+    """torch tensor aliasing the device grid of `agg` (flat, dim 0 of the N-d grid fastest)."""
+    import torch
+    view = _GridView(agg, which)
+    t = torch.as_tensor(view, device=f"cuda:{agg._ctx.device}")
+    t._b200_keepalive = view
+    return t, view.signed_view
+
+
+def slot_stream(ctx, slot=0):
+    """The slot's cudaStream_t as a torch ExternalStream, so NCCL and timing events order after our kernels."""
+    import torch
+    return torch.cuda.ExternalStream(ctx.stream(slot), device=f"cuda:{ctx.device}")
+
+
+def all_reduce_agg(agg, slot=0, group=None):
+    """In-place all-reduce of one aggregator's grid across the ranks of `group`."""
+    import torch
+    import torch.distributed as dist
+    op = agg._op
+    if op == _lib.AGG_FIRST:
+        raise NotImplementedError("first/last across GPUs: reduce (key,row) states with b200_agg_merge on one rank")
+    t, signed_view = grid_tensor(agg)
+    with torch.cuda.stream(slot_stream(agg._ctx, slot)):
+        if op in (_lib.AGG_MIN, _lib.AGG_MAX):
+            if signed_view:  # unsigned min/max through a signed view: flip the sign bit so the order is preserved
+                bias = torch.iinfo(t.dtype).min
+                t.add_(bias)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX if op == _lib.AGG_MAX else dist.ReduceOp.MIN, group=group)
+                t.sub_(bias)
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX if op == _lib.AGG_MAX else dist.ReduceOp.MIN, group=group)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+def all_reduce(aggs, slot=0, group=None):
+    for a in aggs:
+        all_reduce_agg(a, slot, group)
+
+
+def shard_range(nrows, rank, world):
+    """Contiguous row range of `rank` (rows/world each, remainder spread over the first ranks)."""
+    base, rem = divmod(int(nrows), int(world))
+    i1 = rank * base + min(rank, rem)
+    return i1, i1 + base + (1 if rank < rem else 0)
