@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
 
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()
 
 
 def lib():
