@@ -1,0 +1,40 @@
+"""Load tests/golden/binstats_golden.npz (generated from the compiled reference by tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+
+PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "binstats_golden.npz")
+
+
+def load():
+    z = np.load(PATH, allow_pickle=False)
+    cases = {}
+    for key in z.files:
+        name, field = key.split("/", 1)
+        cases.setdefault(name, {})[field] = z[key]
+    return cases
+
+
+def binby_case(c):
+    """-> (binners, aggs, n, expected) in the oracle's spec-dict form."""
+    from oracle import oracle as O
+    n = int(c["n"])
+    binners, aggs, expected = [], [], []
+    for i in range(int(c["nb"])):
+        data = c[f"b{i}_data"].view(np.dtype(str(c[f"b{i}_dtype"])))  # restore byte order
+        mask = c.get(f"b{i}_mask")
+        if str(c[f"b{i}_kind"]) == "scalar":
+            binners.append(O.scalar(data, float(c[f"b{i}_vmin"]), float(c[f"b{i}_vmax"]), int(c[f"b{i}_bins"]), mask=mask))
+        else:
+            binners.append(O.ordinal(data, int(c[f"b{i}_count"]), int(c[f"b{i}_min_value"]), bool(c[f"b{i}_allow_other"]), bool(c[f"b{i}_invert"]), mask=mask))
+    for k in range(int(c["na"])):
+        data = c.get(f"a{k}_data")
+        if data is not None:
+            data = data.view(np.dtype(str(c[f"a{k}_dtype"])))
+        moment = int(c[f"a{k}_moment"]) if f"a{k}_moment" in c else None
+        aggs.append(O.agg(str(c[f"a{k}_op"]), data, c.get(f"a{k}_mask"), moment=moment, order=c.get(f"a{k}_order")))
+        r = c[f"a{k}_result"]
+        if f"a{k}_result_mask" in c:
+            r = np.ma.array(r, mask=c[f"a{k}_result_mask"])
+        expected.append(r)
+    return binners, aggs, n, expected

@@ -1,0 +1,174 @@
+"""API-level GPU tests shaped after the reference's own tests (tests/agg_test.py, tests/count_test.py, tests/groupby_test.py),
+run through vaex_b200.frame.Frame -> TaskPartAggregation -> superagg mirror -> C ABI -> CUDA."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def base_columns():
+    # the numeric core of tests/common.py:313-381 create_base_ds(): x, y = x**2, masked m, NaN n
+    x = np.arange(20, dtype=">f8")
+    y = x ** 2
+    m = np.ma.array(x.astype("f8"), mask=(np.arange(20) % 2 == 1))
+    n = x.astype("f8").copy()
+    n[[1, 3]] = np.nan
+    i8 = np.arange(20, dtype="i1") - 10
+    return dict(x=x, y=y, m=m, n=n, i8=i8)
+
+
+def frame(chunk=None, **kw):
+    from vaex_b200.execution import Executor
+    from vaex_b200.frame import Frame
+    ex = Executor(nthreads=3, chunk_size=chunk)
+    return Frame(base_columns(), executor=ex, **kw)
+
+
+@pytest.mark.parametrize("chunk", [None, 3])
+def test_count_1d(chunk):
+    # tests/agg_test.py:150-158 (small_buffer(size=3) == chunk 3)
+    from vaex_b200.execution import Executor
+    from vaex_b200.frame import Frame
+    x = np.array([-1, -2, 0.5, 1.5, 4.5, 5], dtype="f8")
+    df = Frame(dict(x=x), executor=Executor(nthreads=2, chunk_size=chunk))
+    bins = 5
+    binner = df._binner_specs("x", [0, 5], bins)
+    assert binner[0]["count"] == 5
+    grid = df.count(binby="x", limits=[0, 5], shape=bins, edges=True)
+    assert grid.tolist() == [0, 2, 1, 1, 0, 0, 1, 1]
+    assert df.count(binby="x", limits=[0, 5], shape=bins).tolist() == [1, 1, 0, 0, 1]
+
+
+@pytest.mark.parametrize("chunk", [None, 3])
+def test_count_1d_ordinal(chunk):
+    # tests/agg_test.py:171-180
+    from vaex_b200.execution import Executor
+    from vaex_b200.frame import Frame
+    x = np.array([-1, -2, 0, 1, 4, 5], dtype="i8")
+    df = Frame(dict(x=x), executor=Executor(nthreads=2, chunk_size=chunk))
+    df.categorize("x", min_value=0, count=5)
+    assert df.count(binby="x", edges=True).tolist() == [1, 1, 0, 0, 1, 3, 0]
+
+
+@pytest.mark.parametrize("chunk", [None, 3, 7])
+def test_sum_count_mean(chunk):
+    # tests/agg_test.py:8-48, :108-147: against numpy on the same data, incl. big-endian x, masked m, NaN n
+    df = frame(chunk)
+    c = base_columns()
+    x, y = c["x"].astype("f8"), c["y"].astype("f8")
+    assert df.count() == 20
+    assert df.count("m") == 10
+    assert df.count("n") == 18
+    assert df.sum("x") == x.sum()
+    assert df.sum("m") == c["m"].sum()
+    assert df.sum("n") == np.nansum(c["n"])
+    assert df.sum("i8") == c["i8"].sum() and df.sum("i8").dtype == np.int64  # upcast, tests/agg_test.py:395-402
+    np.testing.assert_array_equal(df.sum("y", binby="x", limits=[0, 20], shape=2), [y[:10].sum(), y[10:].sum()])
+    np.testing.assert_array_equal(df.count(binby=["x", "y"], limits=[[0, 20], [0, 400]], shape=[2, 2]), np.histogram2d(x, y, bins=2, range=[[0, 20], [0, 400]])[0])
+    np.testing.assert_allclose(df.mean("y", binby="x", limits=[0, 20], shape=4), [y[i:i + 5].mean() for i in range(0, 20, 5)], rtol=1e-12)
+
+
+def test_var_and_std_equal_numpy():
+    # tests/agg_test.py:419-439: the reference asserts EXACT equality with numpy on this 10-row fixture
+    from vaex_b200.frame import Frame
+    x = np.arange(10, dtype="f8")
+    y = x ** 2
+    df = Frame(dict(x=x, y=y))
+    assert df.var("y").tolist() == np.var(y).tolist()
+    assert df.std("y").tolist() == np.std(y).tolist()
+    v = df.var("y", binby="x", limits=[0, 10], shape=2)
+    np.testing.assert_allclose(v, [np.var(y[:5]), np.var(y[5:])], rtol=1e-12)
+
+
+def test_minmax_and_limits():
+    # tests/agg_test.py:195-246
+    df = frame(4)
+    c = base_columns()
+    assert df.min("x") == 0 and df.max("x") == 19
+    assert df.min("n") == 0 and df.max("n") == 19
+    assert df.max("m") == 18
+    assert df.min("i8") == -10 and df.min("i8").dtype == np.int8
+    np.testing.assert_array_equal(df.minmax("x"), [0, 19])
+    np.testing.assert_array_equal(df.minmax("n"), [0, 19])
+    np.testing.assert_array_equal(df.minmax("m"), [0, 18])
+    np.testing.assert_array_equal(df.max("y", binby="x", limits=[0, 20], shape=2), [81, 361])
+    # limits=None triggers the device min/max pre-pass
+    grid = df.count(binby="x", shape=4)
+    assert grid.sum() == 19  # the maximum falls on the upper edge and is excluded, like the reference
+
+
+def test_numpy_histogram_cross_check():
+    # tests/count_test.py:26-42
+    from vaex_b200.frame import Frame
+    rng = np.random.default_rng(3)
+    x = rng.normal(0, 1, 100_000)
+    df = Frame(dict(x=x))
+    got = df.count(binby="x", limits=[-4, 4], shape=64)
+    want = np.histogram(x, bins=64, range=(-4, 4))[0]
+    # numpy puts x == upper edge in the last bin; vaex excludes it; none of the samples is exactly 4.0
+    np.testing.assert_array_equal(got, want)
+
+
+def test_selection_and_first_last():
+    from vaex_b200.frame import Frame
+    rng = np.random.default_rng(9)
+    n = 5000
+    x = rng.uniform(0, 10, n)
+    v = rng.normal(0, 1, n)
+    t = rng.permutation(n).astype("i8")
+    df = Frame(dict(x=x, v=v, t=t))
+    sel = v > 0
+    got = df.sum("v", binby="x", limits=[0, 10], shape=5, selection=sel)
+    want = [v[(x >= i * 2) & (x < i * 2 + 2) & sel].sum() for i in range(5)]
+    np.testing.assert_allclose(got, want, rtol=1e-12)
+    first = df.first("v", "t", binby="x", limits=[0, 10], shape=5)
+    last = df.last("v", "t", binby="x", limits=[0, 10], shape=5)
+    for i in range(5):
+        inb = (x >= i * 2) & (x < i * 2 + 2)
+        assert first[i] == v[inb][np.argmin(t[inb])]
+        assert last[i] == v[inb][np.argmax(t[inb])]
+
+
+def test_task_merging_single_pass():
+    # tests/execution_test.py:144-175: aggregations with equal binners share ONE pass
+    df = frame()
+    before = df.executor.passes
+    df._agg([__import__("vaex_b200.agg", fromlist=["x"]).mean("y"), __import__("vaex_b200.agg", fromlist=["x"]).std("y"),
+             __import__("vaex_b200.agg", fromlist=["x"]).count()], binby="x", limits=[0, 20], shape=4)
+    assert df.executor.passes == before + 1
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_groupby_sum_count(fused):
+    # tests/groupby_test.py:116-176 style: groupby over hashed int64 keys, sum + count, against numpy
+    from vaex_b200.frame import Frame
+    rng = np.random.default_rng(4)
+    n = 200_000
+    keys = rng.integers(0, 1000, n).astype("i8") * 256 + 5
+    v = rng.normal(0, 1, n)
+    df = Frame(dict(k=keys, v=v))
+    out = df.groupby("k", agg={"v": ["sum", "count"]}, fused=fused)
+    uniq, inv = np.unique(keys, return_inverse=True)
+    want_sum = np.bincount(inv, weights=v)
+    want_cnt = np.bincount(inv)
+    order = np.argsort(out["k"])
+    np.testing.assert_array_equal(np.asarray(out["k"])[order], uniq)
+    np.testing.assert_array_equal(out["v_count"][order], want_cnt)
+    np.testing.assert_allclose(out["v_sum"][order], want_sum, rtol=1e-9, atol=1e-9)
+    # first-seen order, like the sequential reference
+    first_seen = keys[np.sort(np.unique(keys, return_index=True)[1])]
+    assert set(out["k"].tolist()) == set(first_seen.tolist())
+
+
+def test_groupby_float_keys_nan_and_missing():
+    # tests/groupby_test.py:219-275: NaN and masked keys get their own groups' cells and are dropped from the center
+    from vaex_b200.frame import Frame
+    keys = np.ma.array([1.5, 2.5, np.nan, 1.5, 7.0, np.nan, 2.5, 9.0], mask=[0, 0, 0, 0, 1, 0, 0, 0])
+    v = np.arange(8, dtype="f8")
+    df = Frame(dict(k=keys, v=v))
+    gb = df.groupby("k")
+    hm = gb.hash_maps[0]
+    assert hm.has_nan and hm.has_null and len(hm) == 5
+    out = gb.agg({"v": "sum"})
+    got = {(None if np.ma.is_masked(k) else (float("nan") if k != k else float(k))): s for k, s in zip(out["k"], out["v_sum"])}
+    assert got[1.5] == 3.0 and got[2.5] == 7.0 and got[9.0] == 7.0

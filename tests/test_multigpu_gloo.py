@@ -1,0 +1,86 @@
+"""The N>1 path on CPU: world_size-2 `gloo` run of the row-sharding + grid all-reduce logic (vaex_b200.engine), with the
+oracle standing in for the per-rank kernel.  Checks that shard ranges tile the rows and that sum / min / max grids reduce
+to exactly what one pass over all rows gives."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    from vaex_b200 import _lib, engine
+    rng = np.random.default_rng(123)  # every rank generates the same full columns, then takes its shard
+    x = rng.normal(0, 1, n).astype("f4")
+    y = rng.normal(0, 1, n).astype("f4")
+    v = rng.normal(0, 1, n)
+    u = rng.integers(0, 2 ** 32 - 1, n).astype("u4")
+    i1, i2 = engine.shard_range(n, rank, world)
+    b = [O.scalar(x[i1:i2], -3, 3, 32), O.scalar(y[i1:i2], -3, 3, 32)]
+    aggs = [O.agg("count"), O.agg("sum", v[i1:i2]), O.agg("min", v[i1:i2]), O.agg("max", v[i1:i2]), O.agg("max", u[i1:i2]), O.agg("min", u[i1:i2])]
+    ops = [_lib.AGG_COUNT, _lib.AGG_SUM, _lib.AGG_MIN, _lib.AGG_MAX, _lib.AGG_MAX, _lib.AGG_MIN]
+    grids = O.binby(b, aggs, i2 - i1)
+    reduced = []
+    for g, op in zip(grids, ops):
+        flat = np.ascontiguousarray(g.reshape(-1, order="F"))
+        unsigned = flat.dtype.kind == "u"
+        t = torch.from_numpy(flat.view("i4") if unsigned else flat)
+        engine.all_reduce_tensor(t, op, unsigned_as_signed=unsigned)
+        reduced.append(t.numpy().view(flat.dtype) if unsigned else t.numpy())
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "reduced.npz"), *reduced)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_ranges_tile_rows():
+    sys.path.insert(0, ROOT)
+    from vaex_b200 import engine
+    for n in (0, 1, 7, 1000, 10 ** 10 + 3):
+        for world in (1, 2, 3, 8):
+            r = [engine.shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_gloo_allreduce_matches_single_pass(tmp_path):
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    n, world = 40_001, 2
+    mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    z = np.load(tmp_path / "reduced.npz")
+    reduced = [z[k] for k in z.files]
+    rng = np.random.default_rng(123)
+    x = rng.normal(0, 1, n).astype("f4")
+    y = rng.normal(0, 1, n).astype("f4")
+    v = rng.normal(0, 1, n)
+    u = rng.integers(0, 2 ** 32 - 1, n).astype("u4")
+    b = [O.scalar(x, -3, 3, 32), O.scalar(y, -3, 3, 32)]
+    aggs = [O.agg("count"), O.agg("sum", v), O.agg("min", v), O.agg("max", v), O.agg("max", u), O.agg("min", u)]
+    want = [g.reshape(-1, order="F") for g in O.binby(b, aggs, n)]
+    assert np.array_equal(reduced[0], want[0])                      # counts: bit-exact
+    assert np.allclose(reduced[1], want[1], rtol=1e-12, atol=1e-12)  # fp64 sums: order of addition differs
+    for k in (2, 3, 4, 5):
+        assert np.array_equal(reduced[k], want[k]), k                # min/max incl. unsigned through the signed view

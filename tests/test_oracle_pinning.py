@@ -1,0 +1,88 @@
+"""Pin the oracle (oracle/binstats_oracle.c) — CPU only.
+
+ 1. against the golden vectors generated from the compiled, unmodified reference (tests/golden/, always available);
+ 2. against the compiled reference itself (oracle/_ref) on fresh random cases when it is present in this container.
+The oracle is the checker of every GPU parity test, so it has to be right first."""
+import numpy as np
+import pytest
+
+import golden_util
+from helpers import random_case, same
+
+GOLD = golden_util.load()
+BINBY = sorted(k for k in GOLD if not k.startswith(("set_", "hash64")))
+SETS = sorted(k for k in GOLD if k.startswith("set_"))
+
+
+@pytest.mark.parametrize("name", BINBY)
+def test_oracle_matches_golden_binby(name, oracle):
+    binners, aggs, n, expected = golden_util.binby_case(GOLD[name])
+    got = oracle.binby(binners, aggs, n)
+    for a, w, g in zip(aggs, expected, got):
+        assert same(w, g), (name, a["op"])
+
+
+def test_golden_kats_are_the_reference_test_vectors():
+    # /root/reference/tests/agg_test.py:150-158 and :171-180
+    assert GOLD["kat_count_1d"]["a0_result"].tolist() == [0, 2, 1, 1, 0, 0, 1, 1]
+    assert GOLD["kat_count_1d_ordinal"]["a0_result"].tolist() == [1, 1, 0, 0, 1, 3, 0]
+
+
+@pytest.mark.parametrize("name", SETS)
+def test_oracle_matches_golden_sets(name, oracle):
+    c = GOLD[name]
+    dtype, nmaps = name.split("_")[1], int(name.split("_")[2])
+    s = oracle.OrderedSet(dtype, nmaps)
+    vals, mi = s.update(c["keys"], c["mask"], 0, True)
+    assert np.array_equal(vals, c["values"]) and np.array_equal(mi, c["map_index"])
+    assert np.array_equal(s.key_array(), c["key_array"], equal_nan=True)
+    assert s.offsets() == c["offsets"].tolist()
+    mo = s.map_ordinal(c["keys"])
+    assert mo.dtype == c["map_ordinal"].dtype and np.array_equal(mo, c["map_ordinal"])
+    assert [s.null_index, s.nan_index, s.null_count, s.nan_count] == c["null_nan"].tolist()
+
+
+def test_hash64_golden(oracle):
+    for i, o in zip(GOLD["hash64"]["in"], GOLD["hash64"]["out"]):
+        assert oracle.hash64(int(i)) == int(o)
+    assert oracle.hash64(1) == 6238072747940578789  # SURVEY.md 8c pin
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_matches_compiled_reference_random(seed, oracle, ref):
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 5000))
+    binners, aggs = random_case(rng, n)
+    want = ref.binby(binners, aggs, n)
+    got = oracle.binby(binners, aggs, n)
+    for a, w, g in zip(aggs, want, got):
+        assert same(np.asarray(w) if not np.ma.isMaskedArray(w) else w, g), (a["op"], None if a["data"] is None else a["data"].dtype)
+
+
+def test_oracle_first_mask_quirk_matches_reference(oracle, ref):
+    """AggFirst indexes its mask inside the 1024-row block without the block offset (src/agg_first.cpp:131);
+    the oracle restates that, so both agree even past 1024 rows."""
+    rng = np.random.default_rng(77)
+    n = 3000
+    x = rng.uniform(0, 4, n)
+    v = rng.normal(0, 1, n)
+    o = rng.integers(0, 100, n).astype("i8")
+    m = (rng.random(n) < 0.6).astype("u1")
+    b = [oracle.scalar(x, 0, 4, 4)]
+    a = [oracle.agg("first", v, m, order=o), oracle.agg("last", v, m, order=o)]
+    for w, g in zip(ref.binby(b, a, n), oracle.binby(b, a, n)):
+        assert same(w, g)
+
+
+@pytest.mark.parametrize("nthreads", [1, 4])
+def test_reference_chunk_loop_is_thread_invariant_for_counts(nthreads, oracle, ref):
+    """the restated executor loop (1M-row chunks, per-thread grids folded in get_result) gives the same exact counts"""
+    rng = np.random.default_rng(5)
+    n = 300_000
+    x = rng.normal(0, 1, n).astype("f4")
+    y = rng.normal(0, 1, n).astype("f4")
+    b = [oracle.scalar(x, -3, 3, 64), oracle.scalar(y, -3, 3, 64)]
+    a = [oracle.agg("count")]
+    want = oracle.binby(b, a, n)[0]
+    got = ref.RefBinby(b, a, nthreads).run(n, chunk=50_000)[0]
+    assert np.array_equal(want, np.asarray(got))

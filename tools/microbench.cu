@@ -148,10 +148,22 @@ int main() {
         printf("RED.ADD.32   cells %10llu (%7.1f MB): %8.3f ms  %.3e lanes/s\n", (unsigned long long)cells, cells * 4 / 1e6, ms, lanes / ms * 1e3);
         CK(cudaFree(g64));
     }
-    {
+    {   // is the RED rate an SM-side or an L2-side limit?  shrink the number of SMs issuing
         uint64_t cells = 1 << 20;
         unsigned long long *g64;
         CK(cudaMalloc(&g64, cells * 8));
+        for (int nsm : {37, 74, 111, 148}) {
+            int b = nsm * 8; // 8 CTAs x 256 thr = one full SM each; the block scheduler spreads CTAs one per SM first
+            double l = (double)threads * b * iters;
+            float ms = time_ms([&] { k_red_pow2<unsigned long long><<<b, threads>>>(g64, cells - 1, iters); });
+            printf("RED.ADD.64 pow2 1M cells, %4d CTAs (~%d SMs x8): %8.3f ms  %.3e lanes/s\n", b, nsm, ms, l / ms * 1e3);
+        }
+        for (int nsm : {37, 74, 148}) {
+            int b = nsm; // one CTA per SM -> all SMs busy but 1/8 of the warps
+            double l = (double)threads * b * iters;
+            float ms = time_ms([&] { k_red_pow2<unsigned long long><<<b, threads>>>(g64, cells - 1, iters); });
+            printf("RED.ADD.64 pow2 1M cells, %4d CTAs (1 CTA/SM):   %8.3f ms  %.3e lanes/s\n", b, ms, l / ms * 1e3);
+        }
         for (int occ : {2, 4, 8}) {
             int b = sms * occ;
             double l = (double)threads * b * iters;
@@ -165,8 +177,11 @@ int main() {
     {
         unsigned *out;
         CK(cudaMalloc(&out, blocks * 8));
-        for (int cells : {131, 4096, 16384}) {
-            float ms = time_ms([&] { k_atoms<unsigned><<<blocks, threads, cells * 4>>>(cells, iters, out); });
+        CK(cudaFuncSetAttribute(k_atoms<unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        for (int cells : {131, 4096, 16384, 49152}) {
+            int b2 = cells * 4 > 100 * 1024 ? sms : (cells * 4 > 48 * 1024 ? sms * 2 : blocks);
+            double lanes = (double)threads * b2 * iters;
+            float ms = time_ms([&] { k_atoms<unsigned><<<b2, threads, cells * 4>>>(cells, iters, out); });
             printf("ATOMS.ADD.32 cells %6d: %8.3f ms  %.3e lanes/s  %.2f lanes/clk/SM@1.9GHz\n", cells, ms, lanes / ms * 1e3, lanes / ms * 1e3 / sms / 1.9e9);
         }
         CK(cudaFuncSetAttribute(k_atoms<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));

@@ -47,25 +47,33 @@ def slot_stream(ctx, slot=0):
     return torch.cuda.ExternalStream(ctx.stream(slot), device=f"cuda:{ctx.device}")
 
 
-def all_reduce_agg(agg, slot=0, group=None):
-    """In-place all-reduce of one aggregator's grid across the ranks of `group`."""
+def all_reduce_tensor(t, op, unsigned_as_signed=False, group=None):
+    """All-reduce one flat grid tensor in place.  `op` is the aggregator op (AGG_*): sum-like grids add, min/max grids take
+    the extremum.  Backend agnostic (NCCL on the GPUs; gloo in the CPU tests of the sharding logic)."""
     import torch
     import torch.distributed as dist
-    op = agg._op
-    if op == _lib.AGG_FIRST:
+    if op in (_lib.AGG_MIN, _lib.AGG_MAX):
+        rop = dist.ReduceOp.MAX if op == _lib.AGG_MAX else dist.ReduceOp.MIN
+        if unsigned_as_signed:  # unsigned min/max through a signed view: flip the sign bit so the order is preserved
+            bias = torch.iinfo(t.dtype).min
+            t.add_(bias)
+            dist.all_reduce(t, op=rop, group=group)
+            t.sub_(bias)
+        else:
+            dist.all_reduce(t, op=rop, group=group)
+    elif op in (_lib.AGG_FIRST, _lib.AGG_LAST):
         raise NotImplementedError("first/last across GPUs: reduce (key,row) states with b200_agg_merge on one rank")
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def all_reduce_agg(agg, slot=0, group=None):
+    """In-place all-reduce of one aggregator's device grid across the ranks of `group` (ordered after the slot's kernels)."""
+    import torch
     t, signed_view = grid_tensor(agg)
     with torch.cuda.stream(slot_stream(agg._ctx, slot)):
-        if op in (_lib.AGG_MIN, _lib.AGG_MAX):
-            if signed_view:  # unsigned min/max through a signed view: flip the sign bit so the order is preserved
-                bias = torch.iinfo(t.dtype).min
-                t.add_(bias)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX if op == _lib.AGG_MAX else dist.ReduceOp.MIN, group=group)
-                t.sub_(bias)
-            else:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX if op == _lib.AGG_MAX else dist.ReduceOp.MIN, group=group)
-        else:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        all_reduce_tensor(t, agg._op, signed_view, group)
 
 
 def all_reduce(aggs, slot=0, group=None):

@@ -1,0 +1,236 @@
+"""A minimal DataFrameLocal-shaped front over the B200 hot path, so the parity tests read like the reference's own.
+
+Covers exactly the callers of the path: ``df.count/sum/mean/std/var/min/max/first/last(binby=...,
+limits=..., shape=...)`` (packages/vaex-core/vaex/dataframe.py:842-1607 -> _compute_agg), ``df.minmax/limits`` (the limits
+pre-pass, dataframe.py:1519-1521, 1926-1928) and ``df.groupby(by).agg({...})`` (vaex/groupby.py, hash ordinal path).
+Columns are plain arrays: numpy (host; streamed in chunks) or device arrays (torch CUDA tensors; one fused pass).
+Expressions are column NAMES only — the expression system is upstream of the path and out of scope.
+"""
+import numpy as np
+
+from . import _lib
+from . import agg as _agg
+from . import execution, taskpart
+from . import hash as _hash
+
+
+def _is_device(x):
+    return hasattr(x, "__cuda_array_interface__") and not isinstance(x, np.ndarray)
+
+
+def _dtype_of(ar):
+    if _is_device(ar):
+        return np.dtype(ar.__cuda_array_interface__["typestr"])
+    return np.asarray(ar).dtype if not np.ma.isMaskedArray(ar) else ar.dtype
+
+
+class Frame:
+    def __init__(self, columns, nthreads=None, executor=None, categories=None):
+        self.columns = dict(columns)
+        self.executor = executor or execution.Executor(nthreads)
+        self.categories = dict(categories or {})  # name -> (min_value, count): ordinal-coded columns (df.categorize)
+        n = {len(v) for v in self.columns.values()}
+        assert len(n) <= 1, "all columns must have equal length"
+        self.length = n.pop() if n else 0
+
+    def __len__(self):
+        return self.length
+
+    def __getitem__(self, name):
+        return self.columns[name]
+
+    def dtypes(self):
+        return {k: _dtype_of(v) for k, v in self.columns.items()}
+
+    def categorize(self, name, min_value=0, count=None):
+        """Mark an integer column as ordinal codes [min_value, min_value+count) -> BinnerOrdinal (dataframe.py:5605-5631)."""
+        if count is None:
+            lo, hi = self.minmax(name)
+            min_value, count = int(lo), int(hi) - int(lo) + 1
+        self.categories[name] = (int(min_value), int(count))
+
+    # ---- limits pre-pass ---------------------------------------------------------------------------------------------
+    def minmax(self, expression):
+        """df.minmax: NaN / masked values ignored (vaexfast OP_MIN_MAX, src/vaexfast.cpp:1089-1101) — on the device."""
+        import ctypes as C
+        col = self.columns[expression]
+        mask = None
+        if not _is_device(col) and np.ma.isMaskedArray(col):
+            mask = _lib.mask_column(np.ma.getmaskarray(col))
+            col = np.ascontiguousarray(col.data)
+        c = _lib.column(col)
+        out = (C.c_double * 2)()
+        ctx = _lib.context()
+        _lib.check(_lib.lib().b200_minmax(ctx._h, 0, c.code, c.byteswap, c.ptr, None if mask is None else mask.ptr, c.length, c.memspace, out))
+        return np.array([out[0], out[1]])
+
+    def limits(self, expressions, value="minmax"):
+        if isinstance(expressions, str):
+            return self.minmax(expressions)
+        return np.array([self.minmax(e) for e in expressions])
+
+    # ---- binned statistics -------------------------------------------------------------------------------------------
+    def _binner_specs(self, binby, limits, shape):
+        if binby is None or binby == []:
+            return []
+        if isinstance(binby, (str, dict)):
+            binby = [binby]
+        nd = len(binby)
+        shapes = [shape] * nd if np.isscalar(shape) else list(shape)
+        if limits is None or isinstance(limits, str):
+            limits = [None] * nd
+        limits = list(limits)
+        if nd == 1 and len(limits) == 2 and np.isscalar(limits[0]):
+            limits = [limits]
+        specs = []
+        for i, b in enumerate(binby):
+            if isinstance(b, dict):  # explicit spec (ordinal / hash binners)
+                specs.append(b)
+                continue
+            dtype = _dtype_of(self.columns[b])
+            if b in self.categories:
+                lo, count = self.categories[b]
+                specs.append({"binner-type": "ordinal", "expression": b, "dtype": dtype.str, "count": count, "minimum": lo, "invert": False})
+                continue
+            lim = limits[i]
+            if lim is None:
+                lim = self.minmax(b)  # the extra pass the reference runs for limits=None (dataframe.py:5618)
+            specs.append({"binner-type": "scalar", "expression": b, "dtype": dtype.str, "count": int(shapes[i]), "minimum": float(lim[0]),
+                          "maximum": float(lim[1])})
+        return specs
+
+    def _agg(self, aggregators, binby=None, limits=None, shape=128, selection=None, edges=False):
+        """Run several aggregators in as few passes as possible (equal binners -> one fused pass); returns their results."""
+        single = not isinstance(aggregators, (list, tuple))
+        aggregators = [aggregators] if single else list(aggregators)
+        specs = self._binner_specs(binby, limits, shape)
+        dtypes = self.dtypes()
+        requests = []
+        for a in aggregators:
+            for prim in a.primitives():
+                prim.edges = edges or prim.edges
+                prim.selection = None if selection is None else "selection"
+                requests.append((specs, prim, selection))
+        tasks, pos = execution.merge_aggregation_tasks(requests, dtypes, self.executor.nthreads)
+        self.executor.execute(self.columns, tasks, self.length)
+        results = []
+        for a in aggregators:
+            grids = []
+            for prim in a.primitives():
+                task, k = pos[id(prim)]
+                grids.append(task.result[k])
+            results.append(a.combine(*grids) if isinstance(a, _agg.AggregatorDescriptorMulti) else grids[0])
+        return results[0] if single else results
+
+    def count(self, expression=None, binby=None, limits=None, shape=128, selection=None, edges=False):
+        return self._agg(_agg.count(expression or "*"), binby, limits, shape, selection, edges)
+
+    def sum(self, expression, binby=None, limits=None, shape=128, selection=None, edges=False):
+        return self._agg(_agg.sum(expression), binby, limits, shape, selection, edges)
+
+    def mean(self, expression, binby=None, limits=None, shape=128, selection=None, edges=False):
+        return self._agg(_agg.mean(expression), binby, limits, shape, selection, edges)
+
+    def var(self, expression, binby=None, limits=None, shape=128, selection=None, edges=False):
+        return self._agg(_agg.var(self._as_float64(expression)), binby, limits, shape, selection, edges)
+
+    def std(self, expression, binby=None, limits=None, shape=128, selection=None, edges=False):
+        return self._agg(_agg.std(self._as_float64(expression)), binby, limits, shape, selection, edges)
+
+    def min(self, expression, binby=None, limits=None, shape=128, selection=None, edges=False):
+        return self._agg(_agg.min(expression), binby, limits, shape, selection, edges)
+
+    def max(self, expression, binby=None, limits=None, shape=128, selection=None, edges=False):
+        return self._agg(_agg.max(expression), binby, limits, shape, selection, edges)
+
+    def first(self, expression, order_expression=None, binby=None, limits=None, shape=128, selection=None, edges=False):
+        return self._agg(_agg.first(expression, order_expression), binby, limits, shape, selection, edges)
+
+    def last(self, expression, order_expression=None, binby=None, limits=None, shape=128, selection=None, edges=False):
+        return self._agg(_agg.last(expression, order_expression), binby, limits, shape, selection, edges)
+
+    def _as_float64(self, expression):
+        """var/std/skew/kurtosis run on ``expression.astype('float64')`` in the reference (vaex/agg.py:429-431)."""
+        col = self.columns[expression]
+        if _dtype_of(col) == np.float64 or _dtype_of(col).kind == "f":
+            return expression  # float32 already accumulates in double: identical result without the cast
+        name = f"astype({expression}, 'float64')"
+        if name not in self.columns:
+            self.columns[name] = col.double() if _is_device(col) else np.asarray(col).astype("float64")
+        return name
+
+    # ---- groupby ------------------------------------------------------------------------------------------------------
+    def groupby(self, by, agg=None, sort=False, fused=True):
+        gb = GroupBy(self, by, sort=sort, fused=fused)
+        return gb.agg(agg) if agg is not None else gb
+
+
+class GroupBy:
+    """df.groupby(key).agg(...) over hashed keys.
+
+    Pass 1: TaskPartHashmapUniqueCreate builds the ordered key set on the device (vaex/groupby.py:298, vaex/cpu.py:285-405).
+    Pass 2: with ``fused=True`` the key column is probed inside the binby kernel (BinnerHash_*), so the ordinal column the
+    reference writes and re-reads (vaex/functions.py:2454-2463 + BinnerOrdinal) never exists; ``fused=False`` reproduces
+    the reference's map_ordinal -> BinnerOrdinal data flow.  Keys come out in ordinal (first-seen) order, or sorted."""
+
+    def __init__(self, df, by, sort=False, fused=True):
+        self.df = df
+        self.by = [by] if isinstance(by, str) else list(by)
+        self.fused = fused
+        self.hash_maps = []
+        for name in self.by:
+            col = df.columns[name]
+            part = taskpart.TaskPartHashmapUniqueCreate(None, name, _dtype_of(col), nthreads=1)
+            # nthreads=1 -> 7 shards, chunks fed in row order: the ordinals of the sequential reference run
+            task = execution.Task(part)
+            ex = execution.Executor(1, chunk_size_max=df.executor.chunk_size_max)
+            ex.execute(df.columns, [task], df.length)
+            hm = task.result
+            if sort:
+                hm = hm.sorted()
+            self.hash_maps.append(hm)
+
+    def keys(self):
+        return [hm.keys() for hm in self.hash_maps]
+
+    def agg(self, actions):
+        """actions: {column: [names]} | {column: name} | [descriptors]; returns dict of arrays (one row per non-empty group)."""
+        df = self.df
+        descs, labels = [], []
+        if isinstance(actions, dict):
+            for col, names in actions.items():
+                for n in ([names] if isinstance(names, str) else names):
+                    descs.append(_agg.aggregates[n](col))
+                    labels.append(f"{col}_{n}")
+        else:
+            for d in actions:
+                descs.append(d)
+                labels.append(f"{d.expressions[0] if d.expressions else 'count'}_{d.short_name}")
+        descs.append(_agg.count("*"))  # the reference adds count(*) to drop empty groups (vaex/groupby.py:688-745)
+        labels.append("__count")
+        columns = dict(df.columns)
+        specs = []
+        for name, hm in zip(self.by, self.hash_maps):
+            dtype = _dtype_of(df.columns[name])
+            if self.fused:
+                specs.append({"binner-type": "hash", "expression": name, "dtype": dtype.str, "hash_map_unique": hm})
+            else:
+                codes = hm.map(df.columns[name])
+                cname = f"_ordinal_values({name})"
+                columns[cname] = codes
+                cdt = _dtype_of(codes)
+                specs.append({"binner-type": "ordinal", "expression": cname, "dtype": cdt.str, "count": len(hm), "minimum": 0, "invert": False})
+        frame = Frame(columns, executor=df.executor)
+        grids = frame._agg(descs, binby=specs, edges=True)
+        # _extract_center (vaex/groupby.py:896-977): drop the null / nan edge cells, keep groups with count > 0
+        center = tuple(slice(0, -2) for _ in self.by)
+        counts = grids[-1][center]
+        keep = counts > 0
+        out = {}
+        mesh = np.meshgrid(*[np.arange(len(hm)) for hm in self.hash_maps], indexing="ij")
+        for name, hm, m in zip(self.by, self.hash_maps, mesh):
+            out[name] = hm.keys()[m[keep]]
+        for label, g in zip(labels[:-1], grids[:-1]):
+            out[label] = g[center][keep]
+        out["count"] = counts[keep]
+        return out
