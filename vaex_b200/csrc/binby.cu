@@ -15,6 +15,8 @@
 //
 // Bound: the scatter.  Large grids issue one L2 RED per row per aggregator; L1TEX/LSU retires ~1 scattered lane
 // per clock per SM, so rows/s <= 148 SMs x f_SM / n_aggs — well below the HBM stream rate for 8-12 B rows.
+#include <stdlib.h>
+
 #include "binby_index.cuh"
 
 namespace b200 {
@@ -248,9 +250,19 @@ int launch_variant(b200_ctx *ctx, cudaStream_t stream, const BinParams &p) {
 
 } // namespace
 
+int try_launch_fast(b200_ctx *ctx, cudaStream_t stream, const BinParams &bp, bool vec, bool *taken); // fast.cu
+
 int launch_binby(b200_ctx *ctx, cudaStream_t stream, const BinParams &p, bool vec) {
     if (p.nrows <= 0)
         return B200_OK;
+    // B200_DISABLE_FAST=1 forces the descriptor-driven kernel (A/B measurements, parity tests of both kernels)
+    static const bool disable_fast = getenv("B200_DISABLE_FAST") && atoi(getenv("B200_DISABLE_FAST")) != 0;
+    if (!disable_fast) {
+        bool taken = false;
+        B200_CHECK(try_launch_fast(ctx, stream, p, vec, &taken));
+        if (taken)
+            return B200_OK;
+    }
     if (p.smem_copies > 0)
         return vec ? launch_variant<true, true>(ctx, stream, p) : launch_variant<false, true>(ctx, stream, p);
     return vec ? launch_variant<true, false>(ctx, stream, p) : launch_variant<false, false>(ctx, stream, p);
