@@ -135,6 +135,28 @@ def test_headline_shape_sample(oracle):
     assert int(got[0].sum()) == n
 
 
+def test_tile_partitioned_count_matches_oracle(oracle):
+    """count(*) on big grids takes the two-kernel tile-partition path (csrc/tilecount.cu) from 2^22 rows on: check it
+    against the oracle for fp32 2-D 1024^2 (33 grid tiles), fp64 3-D 126^3 (65 tiles) and a degenerate distribution that
+    overflows its bucket (falls back to direct REDs for the excess)."""
+    rng = np.random.default_rng(21)
+    n = (1 << 22) + 12345
+    x, y = (rng.normal(0, 1, n).astype("f4") for _ in range(2))
+    x[::50001] = np.nan
+    b = [oracle.scalar(x, -3, 3, 1024), oracle.scalar(y, -3, 3, 1024)]
+    assert np.array_equal(oracle.binby(b, [oracle.agg("count")], n)[0], b200_binby(b, [oracle.agg("count")], n, device=True)[0])
+    a, c, d = (rng.normal(0, 1, n) for _ in range(3))
+    b = [oracle.scalar(a, -3, 3, 126), oracle.scalar(c, -2, 3, 126), oracle.scalar(d, -3, 2, 126)]
+    assert np.array_equal(oracle.binby(b, [oracle.agg("count")], n)[0], b200_binby(b, [oracle.agg("count")], n, device=True)[0])
+    n = 1 << 23
+    x = np.full(n, 0.5, "f4")
+    y = np.full(n, -0.25, "f4")
+    y[: n // 8] = rng.normal(0, 1, n // 8).astype("f4")
+    b = [oracle.scalar(x, -3, 3, 1024), oracle.scalar(y, -3, 3, 1024)]
+    got = b200_binby(b, [oracle.agg("count")], n, device=True)[0]
+    assert np.array_equal(oracle.binby(b, [oracle.agg("count")], n)[0], got) and int(got.sum()) == n
+
+
 def test_large_properties():
     """Full-size style properties that need no oracle: conservation of rows, chunk-sum consistency, idempotent merge."""
     import torch

@@ -217,6 +217,7 @@ int b200_ctx_destroy(b200_ctx *ctx) {
     for (Slot *s : ctx->slots) {
         cudaStreamSynchronize(s->stream);
         cudaFree(s->stage);
+        cudaFree(s->scratch);
         cudaFree(s->dscratch);
         cudaFreeHost(s->pinned);
         cudaEventDestroy(s->h2d_done);
@@ -646,7 +647,7 @@ int b200_bin(b200_ctx *ctx, int slot, const b200_binner *binners, int nbinners, 
             int copies = (int)std::min<size_t>(8, (32 * 1024) / copy);
             p.smem_copies = copies < 1 ? 1 : copies;
         }
-        int rc = launch_binby(ctx, st, p, v);
+        int rc = launch_binby(ctx, sl, p, v);
         p.na = 0;
         return rc;
     };

@@ -251,14 +251,19 @@ int launch_variant(b200_ctx *ctx, cudaStream_t stream, const BinParams &p) {
 } // namespace
 
 int try_launch_fast(b200_ctx *ctx, cudaStream_t stream, const BinParams &bp, bool vec, bool *taken); // fast.cu
+int try_launch_tilecount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool vec, bool *taken);     // tilecount.cu
 
-int launch_binby(b200_ctx *ctx, cudaStream_t stream, const BinParams &p, bool vec) {
+int launch_binby(b200_ctx *ctx, Slot *slot, const BinParams &p, bool vec) {
     if (p.nrows <= 0)
         return B200_OK;
+    cudaStream_t stream = slot->stream;
     // B200_DISABLE_FAST=1 forces the descriptor-driven kernel (A/B measurements, parity tests of both kernels)
     static const bool disable_fast = getenv("B200_DISABLE_FAST") && atoi(getenv("B200_DISABLE_FAST")) != 0;
     if (!disable_fast) {
         bool taken = false;
+        B200_CHECK(try_launch_tilecount(ctx, slot, p, vec, &taken));
+        if (taken)
+            return B200_OK;
         B200_CHECK(try_launch_fast(ctx, stream, p, vec, &taken));
         if (taken)
             return B200_OK;

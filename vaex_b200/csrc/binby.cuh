@@ -62,7 +62,7 @@ struct FirstParams {
     uint8_t *cell_masked;
 };
 
-int launch_binby(b200_ctx *ctx, cudaStream_t stream, const BinParams &p, bool vec);
+int launch_binby(b200_ctx *ctx, Slot *slot, const BinParams &p, bool vec);
 int launch_first(b200_ctx *ctx, cudaStream_t stream, const FirstParams &p, bool vec);
 int launch_fill(cudaStream_t stream, void *ptr, int cell_dtype, uint64_t cells, uint64_t bits);
 int launch_merge(cudaStream_t stream, int op, int cell_dtype, void *dst, const void *src, uint64_t cells);

@@ -75,6 +75,8 @@ struct Slot {
     size_t stage_cap = 0;
     void *pinned = nullptr; // small pinned scratch (results of reductions)
     void *dscratch = nullptr;
+    void *scratch = nullptr; // tilecount buckets
+    size_t scratch_cap = 0;
     std::mutex mu;
 };
 

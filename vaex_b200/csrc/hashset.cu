@@ -106,16 +106,20 @@ __global__ void __launch_bounds__(256) k_set_insert(SetSlot *table, unsigned lon
         uint64_t raw = load_raw1(keys, isz, row);
         bool isnull = from_keys ? (row == from_keys_null_index) : (masks && masks[row]);
         if (isnull) {
-            atomicAdd(ctr + CTR_NULL_COUNT, 1ull);
-            atomicMin(ctr + CTR_NULL_TAG, from_keys ? (unsigned long long)row : (tag_base | null_low));
+            if (!(skip_keys & 2)) { // bit 1: this range is being redone after a table growth — specials were already counted
+                atomicAdd(ctr + CTR_NULL_COUNT, 1ull);
+                atomicMin(ctr + CTR_NULL_TAG, from_keys ? (unsigned long long)row : (tag_base | null_low));
+            }
             continue;
         }
         if (raw_isnan(dtype, raw)) {
-            atomicAdd(ctr + CTR_NAN_COUNT, 1ull);
-            atomicMin(ctr + CTR_NAN_TAG, from_keys ? (unsigned long long)row : (tag_base | nan_low));
+            if (!(skip_keys & 2)) {
+                atomicAdd(ctr + CTR_NAN_COUNT, 1ull);
+                atomicMin(ctr + CTR_NAN_TAG, from_keys ? (unsigned long long)row : (tag_base | nan_low));
+            }
             continue;
         }
-        if (skip_keys)
+        if (skip_keys & 1)
             continue;
         unsigned long long canon = key_canon(dtype, raw);
         unsigned long long tag = tag_base | (unsigned long long)row;
@@ -389,18 +393,21 @@ int set_insert_device(b200_set *s, cudaStream_t st, const void *d_keys, const ui
     const unsigned long long nan_low = use_offsets ? second_low : first_low;
     const int isz = dtype_size(s->dtype);
     const int64_t sub = 1ll << 26;
+    int redo = 0;
     for (int64_t row0 = 0; row0 < nrows;) {
         int64_t n = std::min<int64_t>(sub, nrows - row0);
         k_set_insert<<<nblocks((unsigned long long)n), 256, 0, st>>>(s->table, s->cap - 1, s->d_ctr, s->cap / 2, s->dtype, isz, d_keys, d_masks, row0, n,
-                                                                     tag_base, skip_keys, from_keys_null_index, from_keys ? 1 : 0, nan_low, null_low);
+                                                                     tag_base, skip_keys | redo, from_keys_null_index, from_keys ? 1 : 0, nan_low, null_low);
         B200_CUDA(cudaGetLastError());
         B200_CHECK(read_ctr(s, st, h));
         if (h[CTR_OVERFLOW]) {
             unsigned long long zero = 0;
             B200_CUDA(cudaMemcpyAsync(s->d_ctr + CTR_OVERFLOW, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
             B200_CHECK(set_grow(s, st));
-            continue; // redo this range: inserts are idempotent (CAS claim + atomicMin of the tag)
+            redo = 2; // redo this range: key inserts are idempotent (CAS claim + atomicMin of the tag); NaN/null counting is not
+            continue;
         }
+        redo = 0;
         row0 += n;
     }
     s->dirty = true;
