@@ -41,12 +41,16 @@ struct TileParams {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kRounds = 16;            // rows per thread per tile
-constexpr int kTile = kThreads * kRounds;
+constexpr int kRounds = 16;            // rows per lane per warp tile
+constexpr int kWarpTile = 32 * kRounds; // 512 rows sorted per warp at a time
 constexpr int kTileShift = 15;         // 32768 cells per grid tile
 constexpr int kTileCells = 1 << kTileShift;
 constexpr int kMaxParts = 128;
 constexpr int kSlice = 1 << 21;        // bucket entries per K2 CTA
+constexpr unsigned kChunk = 512;       // bucket entries a warp reserves at a time (>= kWarpTile: any segment fits)
+constexpr unsigned kNone = 0xFFFFFFFFu, kOver = 0xFFFFFFFEu;
+constexpr unsigned long long kNone64 = ~0ull;
+constexpr unsigned short kPad = 0xFFFFu; // padding entry (>= 32768: not a cell)
 
 __device__ __forceinline__ unsigned bin_index(double v, double vmin, double scale, double bins_d, unsigned bins) {
     // identical to fast.cu: one saturating round-down conversion + clamp, NaN tested on `scaled` (src/binners.cpp:13-57)
@@ -71,95 +75,187 @@ __device__ __forceinline__ void load4<double>(const void *p, long long i, double
     out[2] = __longlong_as_double(((long long)b.y << 32) | b.x), out[3] = __longlong_as_double(((long long)b.w << 32) | b.z);
 }
 
+// one warp tile (512 rows): index + rank every row.  FULL tiles carry no per-row validity tests.
+template <typename T, int ND, bool FULL>
+__device__ __forceinline__ void tile_rank(const TileParams &p, long long tbase, long long tend, int lane, unsigned *seg, unsigned packed[kRounds]) {
+#pragma unroll
+    for (int q = 0; q < kRounds / 4; q++) {
+        const long long r0 = tbase + q * 128 + lane * 4;
+        double c[ND][4];
+        if (FULL || r0 + 4 <= tend) {
+#pragma unroll
+            for (int d = 0; d < ND; d++)
+                load4<T>(p.x[d], r0, c[d]);
+        } else {
+#pragma unroll
+            for (int d = 0; d < ND; d++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    c[d][j] = r0 + j < tend ? (double)__ldcs(static_cast<const T *>(p.x[d]) + r0 + j) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            unsigned idx = 0;
+#pragma unroll
+            for (int d = 0; d < ND; d++)
+                idx += bin_index(c[d][j], p.vmin[d], p.scale[d], p.bins_d[d], p.bins[d]) * p.stride[d];
+            // rank inside (warp, grid tile): one shared-memory atomic with return per row.  MATCH.ANY + SHFL ranking kept the
+            // ADU pipe 70 % busy and 7-bit ballot ranking the ALU pipe 60 % busy (profiles/r01_ncu_tilecount_*.txt)
+            if (FULL || r0 + j < tend) {
+                const unsigned slot = atomicAdd(seg + (idx >> kTileShift), 1u);
+                packed[q * 4 + j] = idx | (slot << 22); // idx < 2^22 (<= 128 grid tiles of 2^15 cells): part = idx >> 15
+            } else {
+                packed[q * 4 + j] = 0xFFFFFFFFu;
+            }
+        }
+    }
+}
+
+// ---- TMA staging (cp.async.bulk global -> shared, completion on an mbarrier): each warp keeps the NEXT tile's columns in
+// flight while it sorts the current one.  No registers, no LSU issue slots, and the copy engine sees 2 KB requests.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile("{\n\t"
+                 ".reg .pred P1;\n\t"
+                 "WAIT_LOOP:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+                 "@P1 bra DONE;\n\t"
+                 "bra WAIT_LOOP;\n\t"
+                 "DONE:\n\t"
+                 "}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename T>
+__device__ __forceinline__ void lds4(const T *buf, int i, double out[4]);
+template <>
+__device__ __forceinline__ void lds4<float>(const float *buf, int i, double out[4]) {
+    const float4 a = *reinterpret_cast<const float4 *>(buf + i);
+    out[0] = (double)a.x, out[1] = (double)a.y, out[2] = (double)a.z, out[3] = (double)a.w;
+}
+template <>
+__device__ __forceinline__ void lds4<double>(const double *buf, int i, double out[4]) {
+    const double2 a = *reinterpret_cast<const double2 *>(buf + i), b = *reinterpret_cast<const double2 *>(buf + i + 2);
+    out[0] = a.x, out[1] = a.y, out[2] = b.x, out[3] = b.y;
+}
+
+// full tile whose columns already sit in shared memory (TMA staged)
 template <typename T, int ND>
-__global__ void __launch_bounds__(kThreads) k_tile_partition(const __grid_constant__ TileParams p) {
-    __shared__ unsigned short stage[kTile];
-    __shared__ unsigned char stage_p[kTile];
-    __shared__ unsigned wcnt[kThreads / 32][kMaxParts];
-    __shared__ unsigned total[kMaxParts], segstart[kMaxParts + 1], gbase[kMaxParts];
-    __shared__ unsigned char ovf[kMaxParts];
+__device__ __forceinline__ void tile_rank_staged(const TileParams &p, const T *buf, int lane, unsigned *seg, unsigned packed[kRounds]) {
+#pragma unroll
+    for (int q = 0; q < kRounds / 4; q++) {
+        double c[ND][4];
+#pragma unroll
+        for (int d = 0; d < ND; d++)
+            lds4<T>(buf + d * kWarpTile, q * 128 + lane * 4, c[d]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            unsigned idx = 0;
+#pragma unroll
+            for (int d = 0; d < ND; d++)
+                idx += bin_index(c[d][j], p.vmin[d], p.scale[d], p.bins_d[d], p.bins[d]) * p.stride[d];
+            const unsigned slot = atomicAdd(seg + (idx >> kTileShift), 1u);
+            packed[q * 4 + j] = idx | (slot << 22);
+        }
+    }
+}
+
+template <typename T, int ND, bool TMA>
+__global__ void __launch_bounds__(kThreads, TMA ? 2 : 4) k_tile_partition(const __grid_constant__ TileParams p) {
+    // Every WARP is autonomous: it sorts its own 512-row tile by grid tile and appends the segments itself, so the kernel has
+    // no block-level barrier (only __syncwarp).  Bucket space is handed out in CHUNKS of kChunk entries that a warp owns
+    // exclusively: one global atomic per kChunk entries per (warp, grid tile) instead of one per segment — per-segment
+    // reservations on 33 shared cursors serialised in the L2 at ~11 ns each (profiles/r01_ncu_tilecount_v2.txt).
+    // A chunk's unused tail is padded with kPad entries, which k_tile_count skips.
+    __shared__ unsigned stage_all[kThreads / 32][kWarpTile];          // local(15) | part << 15, sorted by part
+    __shared__ unsigned seg_all[kThreads / 32][kMaxParts];            // count per part -> (after the scan) segment start in the stage
+    __shared__ unsigned long long dst_all[kThreads / 32][kMaxParts];  // bucket entry index of stage[0] for this part (kNone64: direct REDs)
+    __shared__ unsigned base_all[kThreads / 32][kMaxParts];           // current chunk of (warp, part): kNone none yet, kOver = bucket full
+    __shared__ unsigned used_all[kThreads / 32][kMaxParts];           // entries used in the current chunk
+
+    extern __shared__ __align__(128) unsigned char tma_buf[];         // TMA: [warp][2 stages][ND][512] of T
+    __shared__ __align__(8) unsigned long long bars[kThreads / 32][2];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    for (int i = threadIdx.x; i < (kThreads / 32) * kMaxParts; i += kThreads)
-        (&wcnt[0][0])[i] = 0;
-    __syncthreads();
+    unsigned *stage = stage_all[warp], *seg = seg_all[warp], *cbase = base_all[warp], *cused = used_all[warp];
+    unsigned long long *dst = dst_all[warp];
+    T *const mybuf = reinterpret_cast<T *>(tma_buf) + (size_t)warp * 2 * ND * kWarpTile;
+    if (TMA && lane == 0) {
+        mbar_init(&bars[warp][0], 1);
+        mbar_init(&bars[warp][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned short *const buckets = p.buckets;
+    const unsigned long long cap = p.cap;
+    const int nparts = p.nparts;
+    for (int i = lane; i < kMaxParts; i += 32) {
+        seg[i] = 0;
+        cbase[i] = kNone;
+        cused[i] = 0;
+    }
+    __syncwarp();
 
-    const long long ntiles = (p.nrows + kTile - 1) / kTile;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long tbase = p.row0 + tile * kTile;
-        const long long tend = min(p.row0 + p.nrows, tbase + kTile);
-        unsigned packed[kRounds]; // local(15) | part(7) << 15 | slot-in-warp(9) << 22; 0xFFFFFFFF = no row
-        // ---- 1. load + index + warp-level multisplit ---------------------------------------------------------------
+    const long long ntiles = (p.nrows + kWarpTile - 1) / kWarpTile;
+    const long long nfull = p.nrows / kWarpTile; // tiles [0, nfull) are complete
+    const long long wglobal = (long long)blockIdx.x * (kThreads / 32) + warp, wtotal = (long long)gridDim.x * (kThreads / 32);
+    auto issue = [&](long long t, int st) { // lane 0: start the bulk copies of tile t's columns into stage st
+        mbar_expect_tx(&bars[warp][st], (unsigned)(ND * kWarpTile * sizeof(T)));
 #pragma unroll
-        for (int q = 0; q < kRounds / 4; q++) {
-            const long long r0 = tbase + q * (kThreads * 4) + threadIdx.x * 4;
-            double c[ND][4];
-            if (r0 + 4 <= tend) {
-#pragma unroll
-                for (int d = 0; d < ND; d++)
-                    load4<T>(p.x[d], r0, c[d]);
+        for (int d = 0; d < ND; d++)
+            tma_load_1d(mybuf + (st * ND + d) * kWarpTile, static_cast<const T *>(p.x[d]) + p.row0 + t * kWarpTile, (unsigned)(kWarpTile * sizeof(T)), &bars[warp][st]);
+    };
+    int st = 0;
+    unsigned phase0 = 0, phase1 = 0;
+    if (TMA && lane == 0 && wglobal < nfull)
+        issue(wglobal, 0);
+    for (long long tile = wglobal; tile < ntiles; tile += wtotal) {
+        const long long tbase = p.row0 + tile * kWarpTile;
+        const long long tend = min(p.row0 + p.nrows, tbase + kWarpTile);
+        const int nvalid = (int)(tend - tbase);
+        unsigned packed[kRounds]; // idx(22) | slot(10) << 22; 0xFFFFFFFF = no row
+        // ---- 1. (staged) load + bit-exact index + rank ----------------------------------------------------------------------
+        if (TMA) {
+            if (lane == 0 && tile + wtotal < nfull)
+                issue(tile + wtotal, st ^ 1); // prefetch the next tile while this one is processed
+            if (tile < nfull) {
+                mbar_wait(&bars[warp][st], st ? phase1 : phase0);
+                if (st)
+                    phase1 ^= 1;
+                else
+                    phase0 ^= 1;
+                tile_rank_staged<T, ND>(p, mybuf + st * ND * kWarpTile, lane, seg, packed);
+                __syncwarp();
+                fence_proxy_async(); // our generic-proxy reads of this stage are done before the copy engine refills it
             } else {
-#pragma unroll
-                for (int d = 0; d < ND; d++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        c[d][j] = r0 + j < tend ? (double)__ldcs(static_cast<const T *>(p.x[d]) + r0 + j) : 0.0;
+                tile_rank<T, ND, false>(p, tbase, tend, lane, seg, packed);
             }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const bool valid = r0 + j < tend;
-                unsigned idx = 0;
-#pragma unroll
-                for (int d = 0; d < ND; d++)
-                    idx += bin_index(c[d][j], p.vmin[d], p.scale[d], p.bins_d[d], p.bins[d]) * p.stride[d];
-                const unsigned part = idx >> kTileShift;
-                // lanes with the same grid tile: AND of per-bit ballots
-                unsigned peers = __ballot_sync(0xffffffffu, valid);
-                for (int b = 0; b < p.pbits; b++) {
-                    const unsigned bal = __ballot_sync(0xffffffffu, (part >> b) & 1u);
-                    peers &= ((part >> b) & 1u) ? bal : ~bal;
-                }
-                unsigned old = 0;
-                const int leader = __ffs(peers) - 1;
-                if (valid && lane == leader) {
-                    old = wcnt[warp][part];
-                    wcnt[warp][part] = old + __popc(peers);
-                }
-                old = __shfl_sync(0xffffffffu, old, valid ? leader : 0);
-                const unsigned slot = old + __popc(peers & lt_mask);
-                packed[q * 4 + j] = valid ? ((idx & (kTileCells - 1)) | (part << kTileShift) | (slot << 22)) : 0xFFFFFFFFu;
-            }
+            st ^= 1;
+        } else if (nvalid == kWarpTile) {
+            tile_rank<T, ND, true>(p, tbase, tend, lane, seg, packed);
+        } else {
+            tile_rank<T, ND, false>(p, tbase, tend, lane, seg, packed);
         }
-        __syncthreads();
-        // ---- 2. per-tile offsets: warp bases, segment starts, global reservations -----------------------------------
-        if (threadIdx.x < p.nparts) {
-            unsigned acc = 0;
-#pragma unroll
-            for (int w = 0; w < kThreads / 32; w++) {
-                const unsigned t = wcnt[w][threadIdx.x];
-                wcnt[w][threadIdx.x] = acc;
-                acc += t;
-            }
-            total[threadIdx.x] = acc;
-            unsigned g = 0;
-            unsigned char o = 0;
-            if (acc) {
-                g = atomicAdd(p.cursors + threadIdx.x, acc);
-                o = (unsigned long long)g + acc > p.cap;
-                if (o && g <= p.cap)
-                    p.limits[threadIdx.x] = g; // exactly one segment per bucket straddles cap; everything before it is dense
-            }
-            gbase[threadIdx.x] = g;
-            ovf[threadIdx.x] = o;
-        }
-        __syncthreads();
-        if (warp == 0) { // exclusive scan of total[0..nparts) -> segstart (4 entries per lane)
+        __syncwarp();
+        // ---- 2. exclusive scan of the per-part counts (4 parts per lane); place each segment in the warp's current chunk -----
+        {
             unsigned v[4], s = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int i = lane * 4 + k;
-                v[k] = i < p.nparts ? total[i] : 0;
+                v[k] = i < nparts ? seg[i] : 0;
                 s += v[k];
             }
             unsigned incl = s;
@@ -170,49 +266,97 @@ __global__ void __launch_bounds__(kThreads) k_tile_partition(const __grid_consta
                     incl += n;
             }
             unsigned run = incl - s;
+            // which parts need a fresh chunk?  (rare: once per kChunk entries per part)
+            bool fresh[4];
+            unsigned any = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int i = lane * 4 + k;
-                if (i <= p.nparts)
-                    segstart[i] = run;
+                fresh[k] = i < nparts && v[k] && cbase[i] != kOver && (cbase[i] == kNone || cused[i] + v[k] > kChunk);
+                any |= fresh[k];
+            }
+            if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    unsigned need = __ballot_sync(0xffffffffu, fresh[k]);
+                    while (need) {
+                        const int src = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int part = src * 4 + k;
+                        const unsigned ob = cbase[part], ou = cused[part];
+                        if (ob != kNone) // pad the tail of the old chunk
+                            for (unsigned e = ou + lane; e < kChunk; e += 32)
+                                buckets[(unsigned long long)part * cap + ob + e] = kPad;
+                        unsigned nb = 0;
+                        if (lane == 0) {
+                            nb = atomicAdd(p.cursors + part, (unsigned)kChunk);
+                            if ((unsigned long long)nb + kChunk > cap)
+                                nb = kOver; // bucket exhausted: this (warp, part) applies its rows with direct REDs from now on
+                        }
+                        nb = __shfl_sync(0xffffffffu, nb, 0);
+                        __syncwarp();
+                        if (lane == 0) {
+                            cbase[part] = nb;
+                            cused[part] = 0;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = lane * 4 + k;
+                if (i < nparts) {
+                    seg[i] = run;
+                    unsigned long long d = kNone64;
+                    if (v[k] && cbase[i] != kOver) {
+                        d = (unsigned long long)i * cap + cbase[i] + cused[i] - run; // entry index of stage[0] if it belonged to part i
+                        cused[i] += v[k];
+                    }
+                    dst[i] = d;
+                }
                 run += v[k];
             }
         }
-        __syncthreads();
-        // ---- 3. scatter the tile into shared memory, sorted by grid tile -----------------------------------------------
+        __syncwarp();
+        // ---- 3. scatter the tile into the warp's stage, sorted by grid tile ----------------------------------------------
 #pragma unroll
         for (int r = 0; r < kRounds; r++) {
             const unsigned pk = packed[r];
-            if (pk != 0xFFFFFFFFu) {
-                const unsigned part = (pk >> kTileShift) & 127u;
-                const unsigned pos = segstart[part] + wcnt[warp][part] + (pk >> 22);
-                stage[pos] = (unsigned short)(pk & (kTileCells - 1));
-                stage_p[pos] = (unsigned char)part;
-            }
+            if (nvalid == kWarpTile || pk != 0xFFFFFFFFu)
+                stage[seg[(pk >> kTileShift) & 127u] + (pk >> 22)] = pk & 0x3FFFFFu;
         }
-        __syncthreads();
-        // ---- 4. coalesced append of every segment to its bucket -----------------------------------------------------------
-        const int nvalid = (int)(tend - tbase);
-        for (int i = threadIdx.x; i < nvalid; i += kThreads) {
-            const unsigned part = stage_p[i];
-            const unsigned local = stage[i];
-            if (!ovf[part])
-                p.buckets[(unsigned long long)part * p.cap + gbase[part] + (i - segstart[part])] = (unsigned short)local;
+        __syncwarp();
+        // ---- 4. append every segment to its bucket (consecutive lanes -> consecutive 16-bit entries of one segment) -------
+        for (int i = lane; i < nvalid; i += 32) {
+            const unsigned e = stage[i];
+            const unsigned long long d = dst[e >> kTileShift];
+            if (d != kNone64)
+                buckets[d + i] = (unsigned short)(e & (kTileCells - 1));
             else
-                atomicAdd(p.grid + ((unsigned long long)part << kTileShift) + local, 1ull);
+                atomicAdd(p.grid + e, 1ull); // e == flat cell index
         }
-        for (int i = threadIdx.x; i < (kThreads / 32) * kMaxParts; i += kThreads)
-            (&wcnt[0][0])[i] = 0;
-        __syncthreads();
+        __syncwarp();
+        for (int i = lane; i < kMaxParts; i += 32)
+            seg[i] = 0;
+        __syncwarp();
+    }
+    // pad the open chunks so that every reserved chunk is completely written
+    for (int part = 0; part < nparts; part++) {
+        const unsigned ob = cbase[part], ou = cused[part];
+        if (ob != kNone && ob != kOver)
+            for (unsigned e = ou + lane; e < kChunk; e += 32)
+                buckets[(unsigned long long)part * cap + ob + e] = kPad;
     }
 }
+
 
 __global__ void __launch_bounds__(1024) k_tile_count(const __grid_constant__ TileParams p, int nslices) {
     extern __shared__ __align__(16) unsigned hist[];
     const int part = blockIdx.x / nslices, slice = blockIdx.x % nslices;
     unsigned long long n = p.cursors[part];
-    if (n > p.cap) // the excess was applied with direct REDs by k_tile_partition; valid entries end at the straddling segment
-        n = min((unsigned long long)p.limits[part], p.cap);
+    if (n > p.cap) // chunks past cap were refused (those rows were applied with direct REDs); cap is a multiple of kChunk
+        n = p.cap;
     const unsigned long long begin = (unsigned long long)slice * kSlice;
     if (begin >= n)
         return;
@@ -225,17 +369,19 @@ __global__ void __launch_bounds__(1024) k_tile_count(const __grid_constant__ Til
     const uint4 *v = reinterpret_cast<const uint4 *>(src + begin);
     for (unsigned long long i = threadIdx.x; i < nvec; i += blockDim.x) {
         const uint4 a = __ldcs(v + i);
-        atomicAdd(hist + (a.x & 0xffffu), 1u);
-        atomicAdd(hist + (a.x >> 16), 1u);
-        atomicAdd(hist + (a.y & 0xffffu), 1u);
-        atomicAdd(hist + (a.y >> 16), 1u);
-        atomicAdd(hist + (a.z & 0xffffu), 1u);
-        atomicAdd(hist + (a.z >> 16), 1u);
-        atomicAdd(hist + (a.w & 0xffffu), 1u);
-        atomicAdd(hist + (a.w >> 16), 1u);
+        const unsigned w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned lo = w[k] & 0xffffu, hi = w[k] >> 16;
+            if (lo < (unsigned)kTileCells) // skip chunk padding
+                atomicAdd(hist + lo, 1u);
+            if (hi < (unsigned)kTileCells)
+                atomicAdd(hist + hi, 1u);
+        }
     }
     for (unsigned long long i = begin + nvec * 8 + threadIdx.x; i < end; i += blockDim.x)
-        atomicAdd(hist + src[i], 1u);
+        if (src[i] < kTileCells)
+            atomicAdd(hist + src[i], 1u);
     __syncthreads();
     const unsigned long long cell0 = (unsigned long long)part << kTileShift;
     for (int i = threadIdx.x; i < kTileCells; i += blockDim.x) {
@@ -245,15 +391,32 @@ __global__ void __launch_bounds__(1024) k_tile_count(const __grid_constant__ Til
     }
 }
 
-template <typename T>
-int launch_partition(int nd, int blocks, cudaStream_t st, const TileParams &p) {
-    switch (nd) {
-    case 1: k_tile_partition<T, 1><<<blocks, kThreads, 0, st>>>(p); break;
-    case 2: k_tile_partition<T, 2><<<blocks, kThreads, 0, st>>>(p); break;
-    default: k_tile_partition<T, 3><<<blocks, kThreads, 0, st>>>(p); break;
+template <typename T, int ND>
+int launch_partition_nd(int sm_count, long long nrows, cudaStream_t st, const TileParams &p) {
+    // TMA-staged variant when two stages of every warp's tile fit next to the 36 KB of sort state
+    constexpr size_t dyn = (size_t)(kThreads / 32) * 2 * ND * kWarpTile * sizeof(T);
+    constexpr bool tma = dyn <= 128 * 1024;
+    const long long ntiles = (nrows + kWarpTile * (kThreads / 32) - 1) / (kWarpTile * (kThreads / 32));
+    if (tma) {
+        auto kern = k_tile_partition<T, ND, tma>;
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        const int blocks = (int)std::min<long long>(ntiles, (long long)sm_count * 2);
+        kern<<<blocks, kThreads, dyn, st>>>(p);
+    } else {
+        const int blocks = (int)std::min<long long>(ntiles, (long long)sm_count * 4);
+        k_tile_partition<T, ND, false><<<blocks, kThreads, 0, st>>>(p);
     }
     B200_CUDA(cudaGetLastError());
     return B200_OK;
+}
+
+template <typename T>
+int launch_partition(int nd, int sm_count, long long nrows, cudaStream_t st, const TileParams &p) {
+    switch (nd) {
+    case 1: return launch_partition_nd<T, 1>(sm_count, nrows, st, p);
+    case 2: return launch_partition_nd<T, 2>(sm_count, nrows, st, p);
+    default: return launch_partition_nd<T, 3>(sm_count, nrows, st, p);
+    }
 }
 
 } // namespace
@@ -295,7 +458,7 @@ int try_launch_tilecount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
     p.grid = static_cast<unsigned long long *>(a.grid);
 
     const long long batch = std::min<long long>(bp.nrows, 1ll << 28);
-    const unsigned long long cap = (((unsigned long long)batch * 4 / nparts + 65536) + 7) / 8 * 8;
+    const unsigned long long cap = (((unsigned long long)batch * 4 / nparts + 65536) + kChunk - 1) / kChunk * kChunk;
     const size_t need = (size_t)nparts * cap * 2 + 4096;
     if (slot->scratch_cap < need) {
         if (slot->scratch) {
@@ -327,12 +490,10 @@ int try_launch_tilecount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
         p.nrows = std::min<long long>(batch, bp.nrows - r0);
         B200_CUDA(cudaMemsetAsync(p.cursors, 0, 2048, st));
         B200_CUDA(cudaMemsetAsync(p.limits, 0xff, 2048, st));
-        const long long ntiles = (p.nrows + kTile - 1) / kTile;
-        const int blocks = (int)std::min<long long>(ntiles, (long long)ctx->sm_count * 6);
         if (t == B200_F32)
-            B200_CHECK(launch_partition<float>(bp.nb, blocks, st, p));
+            B200_CHECK(launch_partition<float>(bp.nb, ctx->sm_count, p.nrows, st, p));
         else
-            B200_CHECK(launch_partition<double>(bp.nb, blocks, st, p));
+            B200_CHECK(launch_partition<double>(bp.nb, ctx->sm_count, p.nrows, st, p));
         k_tile_count<<<nparts * nslices, 1024, kTileCells * 4, st>>>(p, nslices);
         B200_CUDA(cudaGetLastError());
     }
