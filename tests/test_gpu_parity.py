@@ -157,6 +157,23 @@ def test_tile_partitioned_count_matches_oracle(oracle):
     assert np.array_equal(oracle.binby(b, [oracle.agg("count")], n)[0], got) and int(got.sum()) == n
 
 
+def test_interleaved_record_path_matches_oracle(oracle):
+    """mean+std primitives (count, sum, sum^2) on a grid larger than the L2 with many rows per cell take the interleaved
+    32-byte-record accumulation (csrc/fast.cu, k_aos_fold): counts bit-exact, sums within the 1e-6 tolerance."""
+    rng = np.random.default_rng(31)
+    n = 38_000_000
+    x, y, z = (rng.normal(0, 1, n).astype("f4") for _ in range(3))
+    v = rng.normal(0, 1, n).astype("f4")
+    v[::77777] = np.nan
+    b = [oracle.scalar(x, -3, 3, 164), oracle.scalar(y, -3, 3, 164), oracle.scalar(z, -3, 3, 164)]  # 167^3 = 4.66M cells, 3 x 37 MB
+    aggs = [oracle.agg("count", v), oracle.agg("sum", v), oracle.agg("sum_moment", v, moment=2)]
+    want = oracle.binby(b, aggs, n)
+    got = b200_binby(b, aggs, n, device=True)
+    assert np.array_equal(want[0], got[0])
+    for k in (1, 2):
+        assert np.allclose(got[k], want[k], rtol=RTOL, atol=1e-9)
+
+
 def test_large_properties():
     """Full-size style properties that need no oracle: conservation of rows, chunk-sum consistency, idempotent merge."""
     import torch

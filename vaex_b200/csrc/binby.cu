@@ -250,7 +250,7 @@ int launch_variant(b200_ctx *ctx, cudaStream_t stream, const BinParams &p) {
 
 } // namespace
 
-int try_launch_fast(b200_ctx *ctx, cudaStream_t stream, const BinParams &bp, bool vec, bool *taken); // fast.cu
+int try_launch_fast(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool vec, bool *taken);          // fast.cu
 int try_launch_tilecount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool vec, bool *taken);     // tilecount.cu
 
 int launch_binby(b200_ctx *ctx, Slot *slot, const BinParams &p, bool vec) {
@@ -264,7 +264,7 @@ int launch_binby(b200_ctx *ctx, Slot *slot, const BinParams &p, bool vec) {
         B200_CHECK(try_launch_tilecount(ctx, slot, p, vec, &taken));
         if (taken)
             return B200_OK;
-        B200_CHECK(try_launch_fast(ctx, stream, p, vec, &taken));
+        B200_CHECK(try_launch_fast(ctx, slot, p, vec, &taken));
         if (taken)
             return B200_OK;
     }

@@ -101,25 +101,35 @@ __global__ void __launch_bounds__(256) k_set_insert(SetSlot *table, unsigned lon
                                                     int isz, const void *keys, const uint8_t *masks, long long row0, long long nrows,
                                                     unsigned long long tag_base, int skip_keys, long long from_keys_null_index, int from_keys,
                                                     unsigned long long nan_low, unsigned long long null_low) {
+    bool dead = false;
+    unsigned it = 0;
+    // NaN / null bookkeeping is accumulated per thread and published once (same-address atomics serialise in the L2)
+    unsigned long long n_nan = 0, n_null = 0, t_nan = ~0ull, t_null = ~0ull;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += (long long)gridDim.x * blockDim.x) {
+        // once the table overflowed this launch will be redone after a growth: stop inserting (and stop altogether on a redo,
+        // whose NaN/null rows were already counted); the flag is polled every 32 rows per thread
+        if (!dead && (it++ & 31) == 0 && *reinterpret_cast<volatile unsigned long long *>(ctr + CTR_OVERFLOW))
+            dead = true;
+        if (dead && (skip_keys & 2))
+            return;
         const long long row = row0 + i;
         uint64_t raw = load_raw1(keys, isz, row);
         bool isnull = from_keys ? (row == from_keys_null_index) : (masks && masks[row]);
         if (isnull) {
             if (!(skip_keys & 2)) { // bit 1: this range is being redone after a table growth — specials were already counted
-                atomicAdd(ctr + CTR_NULL_COUNT, 1ull);
-                atomicMin(ctr + CTR_NULL_TAG, from_keys ? (unsigned long long)row : (tag_base | null_low));
+                n_null++;
+                t_null = min(t_null, from_keys ? (unsigned long long)row : (tag_base | null_low));
             }
             continue;
         }
         if (raw_isnan(dtype, raw)) {
             if (!(skip_keys & 2)) {
-                atomicAdd(ctr + CTR_NAN_COUNT, 1ull);
-                atomicMin(ctr + CTR_NAN_TAG, from_keys ? (unsigned long long)row : (tag_base | nan_low));
+                n_nan++;
+                t_nan = min(t_nan, from_keys ? (unsigned long long)row : (tag_base | nan_low));
             }
             continue;
         }
-        if (skip_keys & 1)
+        if ((skip_keys & 1) || dead)
             continue;
         unsigned long long canon = key_canon(dtype, raw);
         unsigned long long tag = tag_base | (unsigned long long)row;
@@ -127,8 +137,21 @@ __global__ void __launch_bounds__(256) k_set_insert(SetSlot *table, unsigned lon
             atomicMin(ctr + CTR_SENTINEL_TAG, tag);
             continue;
         }
-        if (!table_insert(table, mask, ctr, max_fill, canon, tag))
-            ctr[CTR_OVERFLOW] = 1ull;
+        if (!table_insert(table, mask, ctr, max_fill, canon, tag)) {
+            // raise the flag ONCE (millions of plain stores to one address serialise in the L2: 0.3 s per overflowed launch in the
+            // first version, profiles/r01_configs_run1.jsonl) and stop: the host grows the table and redoes this range
+            if (!*reinterpret_cast<volatile unsigned long long *>(ctr + CTR_OVERFLOW))
+                ctr[CTR_OVERFLOW] = 1ull;
+            dead = true;
+        }
+    }
+    if (n_null) {
+        atomicAdd(ctr + CTR_NULL_COUNT, n_null);
+        atomicMin(ctr + CTR_NULL_TAG, t_null);
+    }
+    if (n_nan) {
+        atomicAdd(ctr + CTR_NAN_COUNT, n_nan);
+        atomicMin(ctr + CTR_NAN_TAG, t_nan);
     }
 }
 
@@ -393,6 +416,18 @@ int set_insert_device(b200_set *s, cudaStream_t st, const void *d_keys, const ui
     const unsigned long long nan_low = use_offsets ? second_low : first_low;
     const int isz = dtype_size(s->dtype);
     const int64_t sub = 1ll << 26;
+    // size the table for the call up front (every row could be a new key, capped at 2^22 slots = 64 MB): avoids the
+    // grow-and-redo cascade 4K -> 16K -> ... on big inputs; further growth still happens on demand
+    {
+        unsigned long long h0[CTR_N];
+        B200_CHECK(read_ctr(s, st, h0));
+        uint64_t want = s->cap;
+        const uint64_t target = std::min<uint64_t>((uint64_t)(h0[CTR_COUNT] + (unsigned long long)nrows) * 2, 1ull << 22);
+        while (want < target)
+            want <<= 1;
+        while (s->cap < want)
+            B200_CHECK(set_grow(s, st));
+    }
     int redo = 0;
     for (int64_t row0 = 0; row0 < nrows;) {
         int64_t n = std::min<int64_t>(sub, nrows - row0);
