@@ -249,6 +249,8 @@ def run_b200(args):
     assert counted == rows * world, f"row conservation failed: grid holds {counted}, expected {rows * world}"
 
     value = rows * world * args.steps / (total_ms * 1e-3)
+    # count(*) on a 1027^2 grid takes the tile-partition path from 2^22 rows: 2 kernels per batch of <= 2^28 rows
+    launches_per_step = 2 * ((rows + (1 << 28) - 1) >> 28) if rows >= (1 << 22) else 1
     peak, peak_src = measured_peak()
     achieved = BYTES_PER_ROW * rows / (kms * 1e-3) / 1e9
 
@@ -260,10 +262,11 @@ def run_b200(args):
                    "rows_per_gpu": rows, "grid_cells": cells, "parallelism": f"row-shard x{world} + NCCL all-reduce of the int64 grid",
                    "l2": "inputs (8 GB/GPU) far exceed L2; no flush needed", "index_math": "fp64, bit-exact with the reference"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "peak_source": peak_src, "kernel": "k_binby<VEC,global>", "kernel_ms": kms,
-                     "algorithmic_bytes_per_row": BYTES_PER_ROW,
-                     "note": "scatter-bound: one L2 RED per row; see DESIGN.md and profiles/"},
-        "gpu_launches": args.steps * 1,
+                     "peak_source": peak_src, "kernel": "k_tile_partition<float,2,TMA> + k_tile_count (csrc/tilecount.cu)" if rows >= (1 << 22) else "k_binby_fast",
+                     "kernel_ms": kms, "algorithmic_bytes_per_row": BYTES_PER_ROW, "launches_per_step": launches_per_step,
+                     "note": "achieved = 8 B/row x rows per step / device time of the step's binby launches (CUDA events on the launching "
+                             "stream); bound by SM instruction issue in k_tile_partition, not by HBM: see DESIGN.md section 4 and profiles/"},
+        "gpu_launches": args.steps * launches_per_step,
         "clocks": clocks,
     }
 
