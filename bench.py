@@ -55,13 +55,21 @@ class ClockSampler(threading.Thread):
         self.max_mhz = None
         self.stop_flag = threading.Event()
         self.err = None
-
-    def run(self):
-        try:
+        self.nv = self.h = None
+        try:  # NVML is initialised BEFORE the timed region so that the first sample lands inside it
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception as e:  # NVML missing: report that instead of inventing numbers
+            self.err = repr(e)
+
+    def run(self):
+        nv, h = self.nv, self.h
+        if nv is None:
+            return
+        try:
             names = {
                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
@@ -69,14 +77,15 @@ class ClockSampler(threading.Thread):
                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
             }
-            while not self.stop_flag.is_set():
+            while True:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.05)
-        except Exception as e:  # NVML missing: report that instead of inventing numbers
+                if self.stop_flag.wait(0.005):
+                    break
+        except Exception as e:
             self.err = repr(e)
 
     def result(self):
