@@ -173,26 +173,35 @@ __device__ __forceinline__ void tile_rank_staged(const TileParams &p, const T *b
     }
 }
 
+// shared memory per warp: [TMA: 2 stages x ND columns x 512 T] [no TMA: 2 KB stage] [seg | base | used: 128 u32 each] [dst: 128 u64]
 template <typename T, int ND, bool TMA>
-__global__ void __launch_bounds__(kThreads, TMA ? 2 : 4) k_tile_partition(const __grid_constant__ TileParams p) {
+__host__ __device__ constexpr size_t warp_smem_bytes() {
+    return (TMA ? 2 * ND * kWarpTile * sizeof(T) : kWarpTile * sizeof(unsigned)) + 3 * kMaxParts * sizeof(unsigned) + kMaxParts * sizeof(unsigned long long);
+}
+
+template <typename T, int ND, bool TMA, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, TMA ? 2 : 4) k_tile_partition(const __grid_constant__ TileParams p) {
     // Every WARP is autonomous: it sorts its own 512-row tile by grid tile and appends the segments itself, so the kernel has
     // no block-level barrier (only __syncwarp).  Bucket space is handed out in CHUNKS of kChunk entries that a warp owns
     // exclusively: one global atomic per kChunk entries per (warp, grid tile) instead of one per segment — per-segment
-    // reservations on 33 shared cursors serialised in the L2 at ~11 ns each (profiles/r01_ncu_tilecount_v2.txt).
+    // reservations on 33 shared cursors serialised in the L2 at ~11 ns each (profiles/r01_ncu_tile2_*.txt).
     // A chunk's unused tail is padded with kPad entries, which k_tile_count skips.
-    __shared__ unsigned stage_all[kThreads / 32][kWarpTile];          // local(15) | part << 15, sorted by part
-    __shared__ unsigned seg_all[kThreads / 32][kMaxParts];            // count per part -> (after the scan) segment start in the stage
-    __shared__ unsigned long long dst_all[kThreads / 32][kMaxParts];  // bucket entry index of stage[0] for this part (kNone64: direct REDs)
-    __shared__ unsigned base_all[kThreads / 32][kMaxParts];           // current chunk of (warp, part): kNone none yet, kOver = bucket full
-    __shared__ unsigned used_all[kThreads / 32][kMaxParts];           // entries used in the current chunk
-
-    extern __shared__ __align__(128) unsigned char tma_buf[];         // TMA: [warp][2 stages][ND][512] of T
-    __shared__ __align__(8) unsigned long long bars[kThreads / 32][2];
+    // With TMA staging the sort stage ALIASES the column buffer that was just consumed (it is only refilled by the copy engine
+    // one iteration later, after a proxy fence), which is what lets 11 warps x 2 CTAs fit next to the double-buffered columns.
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ __align__(8) unsigned long long bars[WARPS][2];
+    constexpr int kThreads = WARPS * 32;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned *stage = stage_all[warp], *seg = seg_all[warp], *cbase = base_all[warp], *cused = used_all[warp];
-    unsigned long long *dst = dst_all[warp];
-    T *const mybuf = reinterpret_cast<T *>(tma_buf) + (size_t)warp * 2 * ND * kWarpTile;
+    constexpr size_t kPerWarp = warp_smem_bytes<T, ND, TMA>();
+    unsigned char *mine = dyn_smem + (size_t)warp * kPerWarp;
+    T *const mybuf = reinterpret_cast<T *>(mine);                         // TMA: [2][ND][512]
+    unsigned char *tables = mine + (TMA ? 2 * ND * kWarpTile * sizeof(T) : kWarpTile * sizeof(unsigned));
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(tables); // bucket entry index of stage[0] per part (kNone64: direct REDs)
+    unsigned *seg = reinterpret_cast<unsigned *>(tables + kMaxParts * 8);  // count per part -> (after the scan) segment start in the stage
+    unsigned *cbase = seg + kMaxParts;                                     // current chunk of (warp, part): kNone none yet, kOver = bucket full
+    unsigned *cused = cbase + kMaxParts;                                   // entries used in the current chunk
+    unsigned *stage = reinterpret_cast<unsigned *>(mine);                 // no TMA: dedicated; TMA: re-pointed per iteration
     if (TMA && lane == 0) {
         mbar_init(&bars[warp][0], 1);
         mbar_init(&bars[warp][1], 1);
@@ -238,10 +247,10 @@ __global__ void __launch_bounds__(kThreads, TMA ? 2 : 4) k_tile_partition(const 
                     phase0 ^= 1;
                 tile_rank_staged<T, ND>(p, mybuf + st * ND * kWarpTile, lane, seg, packed);
                 __syncwarp();
-                fence_proxy_async(); // our generic-proxy reads of this stage are done before the copy engine refills it
             } else {
                 tile_rank<T, ND, false>(p, tbase, tend, lane, seg, packed);
             }
+            stage = reinterpret_cast<unsigned *>(mybuf + st * ND * kWarpTile); // the consumed column buffer becomes the sort stage
             st ^= 1;
         } else if (nvalid == kWarpTile) {
             tile_rank<T, ND, true>(p, tbase, tend, lane, seg, packed);
@@ -340,6 +349,8 @@ __global__ void __launch_bounds__(kThreads, TMA ? 2 : 4) k_tile_partition(const 
         for (int i = lane; i < kMaxParts; i += 32)
             seg[i] = 0;
         __syncwarp();
+        if (TMA)
+            fence_proxy_async(); // our generic-proxy reads/writes of this buffer are done before the copy engine refills it
     }
     // pad the open chunks so that every reserved chunk is completely written
     for (int part = 0; part < nparts; part++) {
@@ -393,18 +404,24 @@ __global__ void __launch_bounds__(1024) k_tile_count(const __grid_constant__ Til
 
 template <typename T, int ND>
 int launch_partition_nd(int sm_count, long long nrows, cudaStream_t st, const TileParams &p) {
-    // TMA-staged variant when two stages of every warp's tile fit next to the 36 KB of sort state
-    constexpr size_t dyn = (size_t)(kThreads / 32) * 2 * ND * kWarpTile * sizeof(T);
-    constexpr bool tma = dyn <= 128 * 1024;
-    const long long ntiles = (nrows + kWarpTile * (kThreads / 32) - 1) / (kWarpTile * (kThreads / 32));
-    if (tma) {
-        auto kern = k_tile_partition<T, ND, tma>;
+    // TMA-staged variant whenever two CTAs of >= 4 warps fit in the 227 KB of an SM; as many warps per CTA as fit (<= 16)
+    constexpr size_t per_warp = warp_smem_bytes<T, ND, true>();
+    constexpr int fit = (int)((113 * 1024 - 256) / per_warp);
+    constexpr int WARPS = fit > 16 ? 16 : fit;
+    if constexpr (WARPS >= 4) {
+        auto kern = k_tile_partition<T, ND, true, WARPS>;
+        constexpr size_t dyn = per_warp * WARPS;
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        const long long ntiles = (nrows + kWarpTile * WARPS - 1) / (kWarpTile * WARPS);
         const int blocks = (int)std::min<long long>(ntiles, (long long)sm_count * 2);
-        kern<<<blocks, kThreads, dyn, st>>>(p);
+        kern<<<blocks, WARPS * 32, dyn, st>>>(p);
     } else {
+        constexpr int W = 8;
+        auto kern = k_tile_partition<T, ND, false, W>;
+        constexpr size_t dyn = warp_smem_bytes<T, ND, false>() * W;
+        const long long ntiles = (nrows + kWarpTile * W - 1) / (kWarpTile * W);
         const int blocks = (int)std::min<long long>(ntiles, (long long)sm_count * 4);
-        k_tile_partition<T, ND, false><<<blocks, kThreads, 0, st>>>(p);
+        kern<<<blocks, W * 32, dyn, st>>>(p);
     }
     B200_CUDA(cudaGetLastError());
     return B200_OK;
