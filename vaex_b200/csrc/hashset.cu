@@ -61,43 +61,32 @@ __device__ __forceinline__ uint64_t load_raw1(const void *data, int isz, long lo
     }
 }
 
-// insert (or touch) one key; returns false when the table is too full
-__device__ __forceinline__ bool table_insert(SetSlot *table, unsigned long long mask, unsigned long long *ctr, unsigned long long max_fill,
-                                             unsigned long long canon, unsigned long long tag) {
+// insert (or touch) one key; returns false when the table is too full.  "Too full" is detected by PROBE LENGTH, not by a fill
+// counter: one shared counter bumped per new key serialises in the L2 at ~16 ns per update (profiles/r01_microbench.txt,
+// 131-cell RED row) — 16 ms per million keys — while a linear-probing table at load <= 0.5 practically never needs more than
+// kMaxProbe steps and one past ~0.85 quickly does.  The bound also makes every probe loop finite by construction.
+constexpr int kMaxProbe = 96;
+__device__ __forceinline__ bool table_insert(SetSlot *table, unsigned long long mask, unsigned long long canon, unsigned long long tag) {
     unsigned long long h = hash64(canon) & mask;
-    while (true) {
+    for (int step = 0; step < kMaxProbe; step++) {
         unsigned long long k = table[h].key;
+        if (k == SET_EMPTY) {
+            k = atomicCAS(&table[h].key, SET_EMPTY, canon);
+            if (k == SET_EMPTY)
+                k = canon;
+        }
         if (k == canon) {
             if (tag < *reinterpret_cast<volatile unsigned long long *>(&table[h].first))
                 atomicMin(&table[h].first, tag);
             return true;
         }
-        if (k == SET_EMPTY) {
-            // reserve a unit of capacity BEFORE claiming the slot, so the table can never fill past max_fill
-            // (an over-full open-addressing table would make the probe loops spin forever)
-            if (*reinterpret_cast<volatile unsigned long long *>(ctr + CTR_COUNT) >= max_fill)
-                return false;
-            if (atomicAdd(ctr + CTR_COUNT, 1ull) >= max_fill) {
-                atomicAdd(ctr + CTR_COUNT, ~0ull); // -1
-                return false;
-            }
-            unsigned long long old = atomicCAS(&table[h].key, SET_EMPTY, canon);
-            if (old == SET_EMPTY) {
-                atomicMin(&table[h].first, tag);
-                return true;
-            }
-            atomicAdd(ctr + CTR_COUNT, ~0ull); // lost the race for this slot: give the reservation back
-            if (old == canon) {
-                atomicMin(&table[h].first, tag);
-                return true;
-            }
-        }
         h = (h + 1) & mask;
     }
+    return false;
 }
 
 // hash_base::_update (src/hash_primitives.hpp:98-295).  from_keys: ordered_set::create (:486-537) where row i IS the ordinal.
-__global__ void __launch_bounds__(256) k_set_insert(SetSlot *table, unsigned long long mask, unsigned long long *ctr, unsigned long long max_fill, int dtype,
+__global__ void __launch_bounds__(256) k_set_insert(SetSlot *table, unsigned long long mask, unsigned long long *ctr, int dtype,
                                                     int isz, const void *keys, const uint8_t *masks, long long row0, long long nrows,
                                                     unsigned long long tag_base, int skip_keys, long long from_keys_null_index, int from_keys,
                                                     unsigned long long nan_low, unsigned long long null_low) {
@@ -137,7 +126,7 @@ __global__ void __launch_bounds__(256) k_set_insert(SetSlot *table, unsigned lon
             atomicMin(ctr + CTR_SENTINEL_TAG, tag);
             continue;
         }
-        if (!table_insert(table, mask, ctr, max_fill, canon, tag)) {
+        if (!table_insert(table, mask, canon, tag)) {
             // raise the flag ONCE (millions of plain stores to one address serialise in the L2: 0.3 s per overflowed launch in the
             // first version, profiles/r01_configs_run1.jsonl) and stop: the host grows the table and redoes this range
             if (!*reinterpret_cast<volatile unsigned long long *>(ctr + CTR_OVERFLOW))
@@ -175,14 +164,24 @@ __global__ void k_set_rehash(const SetSlot *old, unsigned long long old_cap, Set
 }
 
 __global__ void k_set_compact(const SetSlot *table, unsigned long long cap, unsigned long long *ctr, Entry *out, int dtype, int nmaps) {
+    const unsigned lane = threadIdx.x & 31;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (unsigned long long)gridDim.x * blockDim.x) {
-        unsigned long long k = table[i].key;
-        if (k == SET_EMPTY)
-            continue;
-        unsigned long long pos = atomicAdd(ctr + CTR_CURSOR, 1ull);
-        out[pos].hi = key_hash(dtype, k) % (unsigned long long)nmaps;
-        out[pos].tag = table[i].first;
-        out[pos].key = k;
+        const unsigned long long k = table[i].key;
+        const bool occ = k != SET_EMPTY;
+        // one cursor bump per warp, not per occupied slot (same-address atomics serialise in the L2)
+        const unsigned act = __activemask();
+        const unsigned m = __ballot_sync(act, occ);
+        unsigned long long base = 0;
+        const int leader = __ffs(m) - 1;
+        if (occ && (int)lane == leader)
+            base = atomicAdd(ctr + CTR_CURSOR, (unsigned long long)__popc(m));
+        base = __shfl_sync(act, base, leader < 0 ? 0 : leader);
+        if (occ && out) { // out == nullptr: counting pass only
+            const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+            out[pos].hi = key_hash(dtype, k) % (unsigned long long)nmaps;
+            out[pos].tag = table[i].first;
+            out[pos].key = k;
+        }
     }
 }
 
@@ -314,8 +313,12 @@ int set_finalize(b200_set *s) {
     cudaStream_t st = s->ctx->slots[0]->stream;
     unsigned long long h[CTR_N];
     unsigned long long zero = 0;
+    // the insert kernel keeps no fill counter (see table_insert): count the occupied slots first, then compact them
     B200_CUDA(cudaMemcpyAsync(s->d_ctr + CTR_CURSOR, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
+    k_set_compact<<<nblocks(s->cap), 256, 0, st>>>(s->table, s->cap, s->d_ctr, nullptr, s->dtype, s->nmaps);
     B200_CHECK(read_ctr(s, st, h));
+    h[CTR_COUNT] = h[CTR_CURSOR];
+    B200_CUDA(cudaMemcpyAsync(s->d_ctr + CTR_CURSOR, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
     const bool has_nan = h[CTR_NAN_COUNT] > 0, has_null = h[CTR_NULL_COUNT] > 0, has_sent = h[CTR_SENTINEL_TAG] != 0xFFFFFFFFFFFFFFFFULL;
     const unsigned long long n_table = h[CTR_COUNT];
     const unsigned long long E = n_table + has_nan + has_null + has_sent;
@@ -419,10 +422,9 @@ int set_insert_device(b200_set *s, cudaStream_t st, const void *d_keys, const ui
     // size the table for the call up front (every row could be a new key, capped at 2^22 slots = 64 MB): avoids the
     // grow-and-redo cascade 4K -> 16K -> ... on big inputs; further growth still happens on demand
     {
-        unsigned long long h0[CTR_N];
-        B200_CHECK(read_ctr(s, st, h0));
         uint64_t want = s->cap;
-        const uint64_t target = std::min<uint64_t>((uint64_t)(h0[CTR_COUNT] + (unsigned long long)nrows) * 2, 1ull << 22);
+        const uint64_t known = s->dirty ? 0 : (uint64_t)s->n_keys; // exact only right after a finalisation; growth on demand covers the rest
+        const uint64_t target = std::min<uint64_t>((known + (uint64_t)nrows) * 2, 1ull << 22);
         while (want < target)
             want <<= 1;
         while (s->cap < want)
@@ -431,7 +433,7 @@ int set_insert_device(b200_set *s, cudaStream_t st, const void *d_keys, const ui
     int redo = 0;
     for (int64_t row0 = 0; row0 < nrows;) {
         int64_t n = std::min<int64_t>(sub, nrows - row0);
-        k_set_insert<<<nblocks((unsigned long long)n), 256, 0, st>>>(s->table, s->cap - 1, s->d_ctr, s->cap / 2, s->dtype, isz, d_keys, d_masks, row0, n,
+        k_set_insert<<<nblocks((unsigned long long)n), 256, 0, st>>>(s->table, s->cap - 1, s->d_ctr, s->dtype, isz, d_keys, d_masks, row0, n,
                                                                      tag_base, skip_keys | redo, from_keys_null_index, from_keys ? 1 : 0, nan_low, null_low);
         B200_CUDA(cudaGetLastError());
         B200_CHECK(read_ctr(s, st, h));
