@@ -84,7 +84,7 @@ def test_first_last_chunked_with_order(oracle):
     aggs = [oracle.agg("first", v, None, order=order), oracle.agg("last", v, None, order=order)]
     want = oracle.binby(binners, aggs, n)  # sequential, one chunk
     for chunk in (n, 3000, 1024):
-        got = b200_binby(binners, aggs, n, chunk=chunk, device=True)
+        got = b200_binby(binners, aggs, n, chunk=chunk, device=True, nthreads=3)  # 3 slots = 3 streams: pairs are event-chained
         for w, g in zip(want, got):
             assert same(w, g), chunk
 

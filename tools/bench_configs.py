@@ -126,6 +126,7 @@ def main():
         elif cfg == "C4":
             keys = torch.randint(0, 1_000_000, (n,), device="cuda", dtype=torch.int64, generator=gen) * 256 + 5
             v = torch.empty(n, dtype=torch.float64, device="cuda").normal_(generator=gen)
+            torch.cuda.synchronize()  # data generation is asynchronous: keep it out of the timed region
             t0 = time.perf_counter()
             s = superutils.ordered_set_int64(7)
             s.update(keys, -1)

@@ -285,6 +285,8 @@ int b200_agg_create(b200_ctx *ctx, int op, int dtype, int dtype2, int byteswap, 
             e = cudaMalloc(&a->order, n * dtype_size(dtype2));
         if (e == cudaSuccess)
             e = cudaMalloc((void **)&a->cell_masked, n);
+        if (e == cudaSuccess)
+            e = cudaEventCreateWithFlags(&a->chain, cudaEventDisableTiming);
     }
     if (e != cudaSuccess) {
         b200_agg_destroy(a);
@@ -315,6 +317,8 @@ int b200_agg_destroy(b200_agg *a) {
     cudaFree(a->state);
     cudaFree(a->order);
     cudaFree(a->cell_masked);
+    if (a->chain)
+        cudaEventDestroy(a->chain);
     delete a;
     return B200_OK;
 }
@@ -471,7 +475,9 @@ int b200_agg_merge(b200_agg *a, b200_agg *const *others, int nothers) {
         // same-process peers on other devices are read through UVA peer access when enabled; keep it simple: stage through host
         const void *src = o->grid;
         void *tmp = nullptr, *tstate = nullptr, *torder = nullptr, *tmask = nullptr;
-        b200_agg view = *o;
+        b200_agg view; // shallow alias of `o` (b200_agg is not copyable: it owns a mutex)
+        view.ctx = o->ctx, view.op = o->op, view.dtype = o->dtype, view.dtype2 = o->dtype2, view.byteswap = o->byteswap, view.moment = o->moment;
+        view.cells = o->cells, view.cell_dtype = o->cell_dtype, view.grid = o->grid, view.state = o->state, view.order = o->order, view.cell_masked = o->cell_masked;
         if (o->ctx->device != a->ctx->device) {
             const size_t nb = o->cells * dtype_size(o->cell_dtype);
             B200_CUDA(cudaMalloc(&tmp, nb ? nb : 1));
@@ -674,10 +680,14 @@ int b200_bin(b200_ctx *ctx, int slot, const b200_binner *binners, int nbinners, 
             fp.state = static_cast<unsigned long long *>(a->state);
             fp.cell_masked = a->cell_masked;
             bool v = vec && !(reinterpret_cast<uintptr_t>(fp.data) & 15) && !(reinterpret_cast<uintptr_t>(fp.order) & 15);
-            // select+deposit of one aggregator must not interleave with another slot's pair on the same grid
-            B200_CUDA(cudaDeviceSynchronize());
-            B200_CHECK(launch_first(ctx, st, fp, v));
-            B200_CUDA(cudaStreamSynchronize(st));
+            // select+deposit of one aggregator must not interleave with another slot's pair on the same grid: pairs are chained
+            // through an event (stream-ordered across slots, no host or device-wide synchronisation)
+            {
+                std::lock_guard<std::mutex> chain(a->chain_mu);
+                B200_CUDA(cudaStreamWaitEvent(st, a->chain, 0));
+                B200_CHECK(launch_first(ctx, st, fp, v));
+                B200_CUDA(cudaEventRecord(a->chain, st));
+            }
             continue;
         }
         DevAgg &d = p.a[p.na++];

@@ -100,6 +100,8 @@ struct b200_agg {
     void *state = nullptr;  // FIRST/LAST: cells * 16 B {u64 order key, u64 global row}
     void *order = nullptr;  // FIRST/LAST: cells * dtype_size(dtype2) raw order values
     uint8_t *cell_masked = nullptr; // FIRST/LAST
+    cudaEvent_t chain = nullptr;    // FIRST/LAST: completion of the previous select+deposit pair on this grid (any slot)
+    std::mutex chain_mu;
 };
 
 namespace b200 {
