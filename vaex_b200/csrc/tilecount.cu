@@ -30,6 +30,8 @@ struct TileParams {
     unsigned stride[3];
     long long row0, nrows; // batch
     unsigned cells;
+    unsigned tile_cells;          // cells per grid tile (<= 49152, multiple of 8): part = idx / tile_cells, local = idx % tile_cells < 2^16
+    unsigned long long magic;     // ceil(2^42 / tile_cells): part = (idx * magic) >> 42, exact for idx < 2^22
     int nparts, pbits;
     unsigned short *buckets; // nparts * cap entries
     unsigned long long cap;
@@ -43,8 +45,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kRounds = 16;            // rows per lane per warp tile
 constexpr int kWarpTile = 32 * kRounds; // 512 rows sorted per warp at a time
-constexpr int kTileShift = 15;         // 32768 cells per grid tile
-constexpr int kTileCells = 1 << kTileShift;
+constexpr unsigned kMaxTileCells = 49152; // 192 KB of u32 counters in k_tile_count
 constexpr int kMaxParts = 128;
 constexpr int kSlice = 1 << 21;        // bucket entries per K2 CTA
 constexpr unsigned kChunk = 512;       // bucket entries a warp reserves at a time (>= kWarpTile: any segment fits)
@@ -102,8 +103,9 @@ __device__ __forceinline__ void tile_rank(const TileParams &p, long long tbase, 
             // rank inside (warp, grid tile): one shared-memory atomic with return per row.  MATCH.ANY + SHFL ranking kept the
             // ADU pipe 70 % busy and 7-bit ballot ranking the ALU pipe 60 % busy (profiles/r01_ncu_tilecount_*.txt)
             if (FULL || r0 + j < tend) {
-                const unsigned slot = atomicAdd(seg + (idx >> kTileShift), 1u);
-                packed[q * 4 + j] = idx | (slot << 22); // idx < 2^22 (<= 128 grid tiles of 2^15 cells): part = idx >> 15
+                const unsigned part = (unsigned)(((unsigned long long)idx * p.magic) >> 42);
+                const unsigned slot = atomicAdd(seg + part, 1u);
+                packed[q * 4 + j] = (idx - part * p.tile_cells) | (part << 16) | (slot << 23); // local(16) | part(7) | slot(9)
             } else {
                 packed[q * 4 + j] = 0xFFFFFFFFu;
             }
@@ -167,8 +169,9 @@ __device__ __forceinline__ void tile_rank_staged(const TileParams &p, const T *b
 #pragma unroll
             for (int d = 0; d < ND; d++)
                 idx += bin_index(c[d][j], p.vmin[d], p.scale[d], p.bins_d[d], p.bins[d]) * p.stride[d];
-            const unsigned slot = atomicAdd(seg + (idx >> kTileShift), 1u);
-            packed[q * 4 + j] = idx | (slot << 22);
+            const unsigned part = (unsigned)(((unsigned long long)idx * p.magic) >> 42);
+            const unsigned slot = atomicAdd(seg + part, 1u);
+            packed[q * 4 + j] = (idx - part * p.tile_cells) | (part << 16) | (slot << 23);
         }
     }
 }
@@ -179,7 +182,7 @@ __host__ __device__ constexpr size_t warp_smem_bytes() {
     return (TMA ? 2 * ND * kWarpTile * sizeof(T) : kWarpTile * sizeof(unsigned)) + 3 * kMaxParts * sizeof(unsigned) + kMaxParts * sizeof(unsigned long long);
 }
 
-template <typename T, int ND, bool TMA, int WARPS>
+template <typename T, int ND, bool TMA, int WARPS, int PPL>
 __global__ void __launch_bounds__(WARPS * 32, TMA ? 2 : 4) k_tile_partition(const __grid_constant__ TileParams p) {
     // Every WARP is autonomous: it sorts its own 512-row tile by grid tile and appends the segments itself, so the kernel has
     // no block-level barrier (only __syncwarp).  Bucket space is handed out in CHUNKS of kChunk entries that a warp owns
@@ -258,12 +261,12 @@ __global__ void __launch_bounds__(WARPS * 32, TMA ? 2 : 4) k_tile_partition(cons
             tile_rank<T, ND, false>(p, tbase, tend, lane, seg, packed);
         }
         __syncwarp();
-        // ---- 2. exclusive scan of the per-part counts (4 parts per lane); place each segment in the warp's current chunk -----
+        // ---- 2. exclusive scan of the per-part counts (PPL parts per lane: 1 when the grid has <= 32 tiles); place each segment in the warp's current chunk -----
         {
-            unsigned v[4], s = 0;
+            unsigned v[PPL], s = 0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int i = lane * 4 + k;
+            for (int k = 0; k < PPL; k++) {
+                const int i = lane * PPL + k;
                 v[k] = i < nparts ? seg[i] : 0;
                 s += v[k];
             }
@@ -276,22 +279,22 @@ __global__ void __launch_bounds__(WARPS * 32, TMA ? 2 : 4) k_tile_partition(cons
             }
             unsigned run = incl - s;
             // which parts need a fresh chunk?  (rare: once per kChunk entries per part)
-            bool fresh[4];
+            bool fresh[PPL];
             unsigned any = 0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int i = lane * 4 + k;
+            for (int k = 0; k < PPL; k++) {
+                const int i = lane * PPL + k;
                 fresh[k] = i < nparts && v[k] && cbase[i] != kOver && (cbase[i] == kNone || cused[i] + v[k] > kChunk);
                 any |= fresh[k];
             }
             if (__any_sync(0xffffffffu, any)) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
+                for (int k = 0; k < PPL; k++) {
                     unsigned need = __ballot_sync(0xffffffffu, fresh[k]);
                     while (need) {
                         const int src = __ffs(need) - 1;
                         need &= need - 1;
-                        const int part = src * 4 + k;
+                        const int part = src * PPL + k;
                         const unsigned ob = cbase[part], ou = cused[part];
                         if (ob != kNone) // pad the tail of the old chunk
                             for (unsigned e = ou + lane; e < kChunk; e += 32)
@@ -313,8 +316,8 @@ __global__ void __launch_bounds__(WARPS * 32, TMA ? 2 : 4) k_tile_partition(cons
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int i = lane * 4 + k;
+            for (int k = 0; k < PPL; k++) {
+                const int i = lane * PPL + k;
                 if (i < nparts) {
                     seg[i] = run;
                     unsigned long long d = kNone64;
@@ -333,17 +336,18 @@ __global__ void __launch_bounds__(WARPS * 32, TMA ? 2 : 4) k_tile_partition(cons
         for (int r = 0; r < kRounds; r++) {
             const unsigned pk = packed[r];
             if (nvalid == kWarpTile || pk != 0xFFFFFFFFu)
-                stage[seg[(pk >> kTileShift) & 127u] + (pk >> 22)] = pk & 0x3FFFFFu;
+                stage[seg[(pk >> 16) & 127u] + (pk >> 23)] = pk & 0x7FFFFFu;
         }
         __syncwarp();
         // ---- 4. append every segment to its bucket (consecutive lanes -> consecutive 16-bit entries of one segment) -------
         for (int i = lane; i < nvalid; i += 32) {
             const unsigned e = stage[i];
-            const unsigned long long d = dst[e >> kTileShift];
+            const unsigned part = e >> 16;
+            const unsigned long long d = dst[part];
             if (d != kNone64)
-                buckets[d + i] = (unsigned short)(e & (kTileCells - 1));
+                buckets[d + i] = (unsigned short)e;
             else
-                atomicAdd(p.grid + e, 1ull); // e == flat cell index
+                atomicAdd(p.grid + (unsigned long long)part * p.tile_cells + (e & 0xffffu), 1ull);
         }
         __syncwarp();
         for (int i = lane; i < kMaxParts; i += 32)
@@ -372,7 +376,8 @@ __global__ void __launch_bounds__(1024) k_tile_count(const __grid_constant__ Til
     if (begin >= n)
         return;
     const unsigned long long end = min(n, begin + (unsigned long long)kSlice);
-    for (int i = threadIdx.x; i < kTileCells / 4; i += blockDim.x)
+    const unsigned tc = p.tile_cells;
+    for (int i = threadIdx.x; i < (int)(tc / 4); i += blockDim.x)
         reinterpret_cast<uint4 *>(hist)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     const unsigned short *src = p.buckets + (unsigned long long)part * p.cap;
@@ -384,32 +389,32 @@ __global__ void __launch_bounds__(1024) k_tile_count(const __grid_constant__ Til
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const unsigned lo = w[k] & 0xffffu, hi = w[k] >> 16;
-            if (lo < (unsigned)kTileCells) // skip chunk padding
+            if (lo < tc) // skip chunk padding (0xFFFF >= tile_cells)
                 atomicAdd(hist + lo, 1u);
-            if (hi < (unsigned)kTileCells)
+            if (hi < tc)
                 atomicAdd(hist + hi, 1u);
         }
     }
     for (unsigned long long i = begin + nvec * 8 + threadIdx.x; i < end; i += blockDim.x)
-        if (src[i] < kTileCells)
+        if (src[i] < tc)
             atomicAdd(hist + src[i], 1u);
     __syncthreads();
-    const unsigned long long cell0 = (unsigned long long)part << kTileShift;
-    for (int i = threadIdx.x; i < kTileCells; i += blockDim.x) {
+    const unsigned long long cell0 = (unsigned long long)part * tc;
+    for (int i = threadIdx.x; i < (int)tc; i += blockDim.x) {
         const unsigned c = hist[i];
         if (c && cell0 + i < p.cells)
             atomicAdd(p.grid + cell0 + i, (unsigned long long)c);
     }
 }
 
-template <typename T, int ND>
-int launch_partition_nd(int sm_count, long long nrows, cudaStream_t st, const TileParams &p) {
+template <typename T, int ND, int PPL>
+int launch_partition_ppl(int sm_count, long long nrows, cudaStream_t st, const TileParams &p) {
     // TMA-staged variant whenever two CTAs of >= 4 warps fit in the 227 KB of an SM; as many warps per CTA as fit (<= 16)
     constexpr size_t per_warp = warp_smem_bytes<T, ND, true>();
     constexpr int fit = (int)((113 * 1024 - 256) / per_warp);
     constexpr int WARPS = fit > 16 ? 16 : fit;
     if constexpr (WARPS >= 4) {
-        auto kern = k_tile_partition<T, ND, true, WARPS>;
+        auto kern = k_tile_partition<T, ND, true, WARPS, PPL>;
         constexpr size_t dyn = per_warp * WARPS;
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         const long long ntiles = (nrows + kWarpTile * WARPS - 1) / (kWarpTile * WARPS);
@@ -417,7 +422,7 @@ int launch_partition_nd(int sm_count, long long nrows, cudaStream_t st, const Ti
         kern<<<blocks, WARPS * 32, dyn, st>>>(p);
     } else {
         constexpr int W = 8;
-        auto kern = k_tile_partition<T, ND, false, W>;
+        auto kern = k_tile_partition<T, ND, false, W, PPL>;
         constexpr size_t dyn = warp_smem_bytes<T, ND, false>() * W;
         const long long ntiles = (nrows + kWarpTile * W - 1) / (kWarpTile * W);
         const int blocks = (int)std::min<long long>(ntiles, (long long)sm_count * 4);
@@ -425,6 +430,15 @@ int launch_partition_nd(int sm_count, long long nrows, cudaStream_t st, const Ti
     }
     B200_CUDA(cudaGetLastError());
     return B200_OK;
+}
+
+template <typename T, int ND>
+int launch_partition_nd(int sm_count, long long nrows, cudaStream_t st, const TileParams &p) {
+    if (p.nparts <= 32)
+        return launch_partition_ppl<T, ND, 1>(sm_count, nrows, st, p);
+    if (p.nparts <= 64)
+        return launch_partition_ppl<T, ND, 2>(sm_count, nrows, st, p);
+    return launch_partition_ppl<T, ND, 4>(sm_count, nrows, st, p);
 }
 
 template <typename T>
@@ -448,9 +462,20 @@ int try_launch_tilecount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
     if (a.op != B200_AGG_COUNT || a.data || a.mask)
         return B200_OK;
     const unsigned long long cells = bp.cells;
-    const int nparts = (int)((cells + kTileCells - 1) >> kTileShift);
-    if (cells * 4 <= 96 * 1024 || nparts > kMaxParts) // small grids: shared-memory privatisation; huge grids: direct REDs
+    if (cells * 4 <= 96 * 1024 || cells > (unsigned long long)kMaxTileCells * kMaxParts || cells >= (1ull << 22))
+        return B200_OK; // small grids: shared-memory privatisation; huge grids: direct REDs
+    // as few grid tiles as possible (32, else 64, else 128): the per-tile bookkeeping of k_tile_partition scales with tiles per lane
+    unsigned tile_cells = 0;
+    for (int np = 32; np <= kMaxParts; np *= 2) {
+        const unsigned long long tcells = ((cells + np - 1) / np + 7) / 8 * 8;
+        if (tcells <= kMaxTileCells) {
+            tile_cells = (unsigned)tcells;
+            break;
+        }
+    }
+    if (!tile_cells)
         return B200_OK;
+    const int nparts = (int)((cells + tile_cells - 1) / tile_cells);
     const int t = bp.b[0].dtype;
     if (t != B200_F32 && t != B200_F64)
         return B200_OK;
@@ -468,6 +493,8 @@ int try_launch_tilecount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
         p.stride[i] = (unsigned)b.stride;
     }
     p.cells = (unsigned)cells;
+    p.tile_cells = tile_cells;
+    p.magic = ((1ull << 42) + tile_cells - 1) / tile_cells;
     p.nparts = nparts;
     p.pbits = 0;
     while ((1 << p.pbits) < nparts)
@@ -498,7 +525,7 @@ int try_launch_tilecount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
     cudaStream_t st = slot->stream;
     static bool attr_set = false;
     if (!attr_set) {
-        B200_CUDA(cudaFuncSetAttribute(k_tile_count, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileCells * 4));
+        B200_CUDA(cudaFuncSetAttribute(k_tile_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxTileCells * 4)));
         attr_set = true;
     }
     const int nslices = (int)((cap + kSlice - 1) / kSlice);
@@ -511,7 +538,7 @@ int try_launch_tilecount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
             B200_CHECK(launch_partition<float>(bp.nb, ctx->sm_count, p.nrows, st, p));
         else
             B200_CHECK(launch_partition<double>(bp.nb, ctx->sm_count, p.nrows, st, p));
-        k_tile_count<<<nparts * nslices, 1024, kTileCells * 4, st>>>(p, nslices);
+        k_tile_count<<<nparts * nslices, 1024, (size_t)tile_cells * 4, st>>>(p, nslices);
         B200_CUDA(cudaGetLastError());
     }
     *taken = true;
