@@ -194,6 +194,9 @@ __global__ void __launch_bounds__(WARPS * 32, TMA ? 2 : 4) k_tile_partition(cons
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ __align__(8) unsigned long long bars[WARPS][2];
     constexpr int kThreads = WARPS * 32;
+    // PAIR: every segment is padded to an even length so that the copy-out moves TWO 16-bit entries per lane per step with one
+    // aligned 32-bit store (needs room for 32*PPL pad entries in the stage: every staged variant except 1-D fp32)
+    constexpr bool PAIR = TMA && ND * sizeof(T) >= 8;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr size_t kPerWarp = warp_smem_bytes<T, ND, TMA>();
@@ -262,13 +265,15 @@ __global__ void __launch_bounds__(WARPS * 32, TMA ? 2 : 4) k_tile_partition(cons
         }
         __syncwarp();
         // ---- 2. exclusive scan of the per-part counts (PPL parts per lane: 1 when the grid has <= 32 tiles); place each segment in the warp's current chunk -----
+        unsigned nstage = 0; // entries in the stage incl. fillers
         {
-            unsigned v[PPL], s = 0;
+            unsigned v[PPL], ve[PPL], s = 0;
 #pragma unroll
             for (int k = 0; k < PPL; k++) {
                 const int i = lane * PPL + k;
                 v[k] = i < nparts ? seg[i] : 0;
-                s += v[k];
+                ve[k] = PAIR ? (v[k] + 1u) & ~1u : v[k]; // length the segment occupies in the stage and in its bucket
+                s += ve[k];
             }
             unsigned incl = s;
 #pragma unroll
@@ -278,13 +283,14 @@ __global__ void __launch_bounds__(WARPS * 32, TMA ? 2 : 4) k_tile_partition(cons
                     incl += n;
             }
             unsigned run = incl - s;
+            nstage = __shfl_sync(0xffffffffu, incl, 31);
             // which parts need a fresh chunk?  (rare: once per kChunk entries per part)
             bool fresh[PPL];
             unsigned any = 0;
 #pragma unroll
             for (int k = 0; k < PPL; k++) {
                 const int i = lane * PPL + k;
-                fresh[k] = i < nparts && v[k] && cbase[i] != kOver && (cbase[i] == kNone || cused[i] + v[k] > kChunk);
+                fresh[k] = i < nparts && v[k] && cbase[i] != kOver && (cbase[i] == kNone || cused[i] + ve[k] > kChunk);
                 any |= fresh[k];
             }
             if (__any_sync(0xffffffffu, any)) {
@@ -320,14 +326,16 @@ __global__ void __launch_bounds__(WARPS * 32, TMA ? 2 : 4) k_tile_partition(cons
                 const int i = lane * PPL + k;
                 if (i < nparts) {
                     seg[i] = run;
+                    if (PAIR && (v[k] & 1u))
+                        stage[run + v[k]] = kPad | ((unsigned)i << 16); // the odd segment's filler entry
                     unsigned long long d = kNone64;
                     if (v[k] && cbase[i] != kOver) {
                         d = (unsigned long long)i * cap + cbase[i] + cused[i] - run; // entry index of stage[0] if it belonged to part i
-                        cused[i] += v[k];
+                        cused[i] += ve[k];
                     }
                     dst[i] = d;
                 }
-                run += v[k];
+                run += ve[k];
             }
         }
         __syncwarp();
@@ -340,14 +348,29 @@ __global__ void __launch_bounds__(WARPS * 32, TMA ? 2 : 4) k_tile_partition(cons
         }
         __syncwarp();
         // ---- 4. append every segment to its bucket (consecutive lanes -> consecutive 16-bit entries of one segment) -------
-        for (int i = lane; i < nvalid; i += 32) {
-            const unsigned e = stage[i];
-            const unsigned part = e >> 16;
-            const unsigned long long d = dst[part];
-            if (d != kNone64)
-                buckets[d + i] = (unsigned short)e;
-            else
-                atomicAdd(p.grid + (unsigned long long)part * p.tile_cells + (e & 0xffffu), 1ull);
+        if (PAIR) {
+            for (unsigned i2 = lane; i2 < nstage / 2; i2 += 32) {
+                const uint2 e = *reinterpret_cast<const uint2 *>(stage + 2 * i2); // never straddles two segments (even starts)
+                const unsigned part = e.x >> 16;
+                const unsigned long long d = dst[part];
+                if (d != kNone64) {
+                    *reinterpret_cast<unsigned *>(buckets + d + 2 * i2) = (e.x & 0xffffu) | (e.y << 16);
+                } else {
+                    atomicAdd(p.grid + (unsigned long long)part * p.tile_cells + (e.x & 0xffffu), 1ull);
+                    if ((e.y & 0xffffu) != kPad)
+                        atomicAdd(p.grid + (unsigned long long)part * p.tile_cells + (e.y & 0xffffu), 1ull);
+                }
+            }
+        } else {
+            for (int i = lane; i < nvalid; i += 32) {
+                const unsigned e = stage[i];
+                const unsigned part = e >> 16;
+                const unsigned long long d = dst[part];
+                if (d != kNone64)
+                    buckets[d + i] = (unsigned short)e;
+                else
+                    atomicAdd(p.grid + (unsigned long long)part * p.tile_cells + (e & 0xffffu), 1ull);
+            }
         }
         __syncwarp();
         for (int i = lane; i < kMaxParts; i += 32)
