@@ -47,7 +47,7 @@ constexpr int kRounds = 16;            // rows per lane per warp tile
 constexpr int kWarpTile = 32 * kRounds; // 512 rows sorted per warp at a time
 constexpr unsigned kMaxTileCells = 49152; // 192 KB of u32 counters in k_tile_count
 constexpr int kMaxParts = 128;
-constexpr int kSlice = 1 << 21;        // bucket entries per K2 CTA
+constexpr int kSlice = 1 << 20;        // bucket entries per K2 CTA
 constexpr unsigned kChunk = 512;       // bucket entries a warp reserves at a time (>= kWarpTile: any segment fits)
 constexpr unsigned kNone = 0xFFFFFFFFu, kOver = 0xFFFFFFFEu;
 constexpr unsigned long long kNone64 = ~0ull;
@@ -406,8 +406,7 @@ __global__ void __launch_bounds__(1024) k_tile_count(const __grid_constant__ Til
     const unsigned short *src = p.buckets + (unsigned long long)part * p.cap;
     const unsigned long long nvec = (end - begin) / 8;
     const uint4 *v = reinterpret_cast<const uint4 *>(src + begin);
-    for (unsigned long long i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const uint4 a = __ldcs(v + i);
+    auto apply = [&](const uint4 a) {
         const unsigned w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -417,7 +416,19 @@ __global__ void __launch_bounds__(1024) k_tile_count(const __grid_constant__ Til
             if (hi < tc)
                 atomicAdd(hist + hi, 1u);
         }
+    };
+    // four independent 128-bit loads in flight per thread (one load per step left the SM waiting ~1500 cycles per step)
+    unsigned long long i = threadIdx.x;
+    const unsigned long long stride = blockDim.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        const uint4 a0 = __ldcs(v + i), a1 = __ldcs(v + i + stride), a2 = __ldcs(v + i + 2 * stride), a3 = __ldcs(v + i + 3 * stride);
+        apply(a0);
+        apply(a1);
+        apply(a2);
+        apply(a3);
     }
+    for (; i < nvec; i += stride)
+        apply(__ldcs(v + i));
     for (unsigned long long i = begin + nvec * 8 + threadIdx.x; i < end; i += blockDim.x)
         if (src[i] < tc)
             atomicAdd(hist + src[i], 1u);
