@@ -270,7 +270,11 @@ def run_b200(args):
         "config": {"workload": f"df.count(binby=[x,y], limits=[[-3,3]]*2, shape=1024) on {rows:.3g} fp32 rows per GPU, device-resident columns",
                    "rows_per_gpu": rows, "grid_cells": cells, "parallelism": f"row-shard x{world} + NCCL all-reduce of the int64 grid",
                    "l2": "inputs (8 GB/GPU) far exceed L2; no flush needed", "index_math": "fp64, bit-exact with the reference"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the two kernels of one batch, `ncu --set full` capture
+                     # profiles/r01_ncu_final_tilecount_pair.txt: 3.391 GB per 2.6e8 rows = 13.04 B/row (8 algorithmic + 2 B/row of
+                     # bucket writes + 2 B/row of bucket reads + chunk padding), scaled to the rows of one step
+                     "traffic": (13.04 * rows / 1e9) if rows >= (1 << 22) else None, "traffic_unit": "GB per step",
                      "peak_source": peak_src, "kernel": "k_tile_partition<float,2,TMA> + k_tile_count (csrc/tilecount.cu)" if rows >= (1 << 22) else "k_binby_fast",
                      "kernel_ms": kms, "algorithmic_bytes_per_row": BYTES_PER_ROW, "launches_per_step": launches_per_step,
                      "note": "achieved = 8 B/row x rows per step / device time of the step's binby launches (CUDA events on the launching "
