@@ -84,3 +84,44 @@ def test_two_rank_gloo_allreduce_matches_single_pass(tmp_path):
     assert np.allclose(reduced[1], want[1], rtol=1e-12, atol=1e-12)  # fp64 sums: order of addition differs
     for k in (2, 3, 4, 5):
         assert np.array_equal(reduced[k], want[k]), k                # min/max incl. unsigned through the signed view
+
+
+def _worker_sets(rank, world, port, n, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    from vaex_b200 import engine
+    rng = np.random.default_rng(99)
+    keys = rng.integers(0, 500, n).astype("f8") * 0.5
+    keys[rng.random(n) < 0.01] = np.nan
+    i1, i2 = engine.shard_range(n, rank, world)
+    local = O.OrderedSet("float64", 3)
+    local.update(keys[i1:i2], None, -1, False)
+    union = engine.union_key_sets(local, make_set=lambda: O.OrderedSet("float64", 3))
+    np.save(os.path.join(out_dir, f"keys_{rank}.npy"), union.key_array())
+    codes = union.map_ordinal(keys[i1:i2]).astype(np.int64)
+    counts = torch.from_numpy(np.bincount(codes, minlength=len(union)).astype(np.int64))
+    dist.all_reduce(counts)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "counts.npy"), counts.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_groupby_key_union_gives_identical_ordinals(tmp_path):
+    """pass 1 of a row-sharded groupby: both ranks end up with the same key order, and the all-reduced per-ordinal counts
+    equal a single-process groupby over all rows"""
+    n, world = 30_000, 2
+    mp.spawn(_worker_sets, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    k0, k1 = np.load(tmp_path / "keys_0.npy"), np.load(tmp_path / "keys_1.npy")
+    assert np.array_equal(k0, k1, equal_nan=True)
+    counts = np.load(tmp_path / "counts.npy")
+    rng = np.random.default_rng(99)
+    keys = rng.integers(0, 500, n).astype("f8") * 0.5
+    keys[rng.random(n) < 0.01] = np.nan
+    assert counts.sum() == n
+    for key, c in zip(k0, counts):
+        want = np.isnan(keys).sum() if key != key else (keys == key).sum()
+        assert c == want

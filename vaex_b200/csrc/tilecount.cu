@@ -5,17 +5,19 @@
 // 2-D 1024^2 count at ~1.5e11 rows/s = 18 % of the HBM stream rate.  Shared-memory atomics retire ~6 lanes/clk/SM
 // (profiles/r01_microbench.txt), 9x more — but a 1027^2 grid is 4 MB even with 32-bit counters.
 //
-// Scheme (two kernels per batch of <= 2^28 rows, both on the caller's stream):
-//   K1 k_tile_partition  every CTA takes tiles of 4096 rows: 128-bit coalesced loads, the bit-exact fp64 bin index, then a
-//                        counting sort of the tile by GRID TILE (flat index >> 15, i.e. 32768 consecutive cells) done with warp
-//                        ballots + warp-private counters in shared memory, and one coalesced append of each tile-segment to
-//                        that grid tile's bucket in global memory as 16-bit local indices (2 B/row).
-//   K2 k_tile_count      CTA (tile, slice) zeroes a private 32768-cell u32 histogram in shared memory (128 KB), streams its
+// Scheme (two kernels per batch of <= 2^28 rows, both on the caller's stream); the grid is cut into <= 32 (else 64 / 128)
+// GRID TILES of <= 49152 consecutive cells (1027^2 -> 32 tiles of 32,961 cells):
+//   K1 k_tile_partition  every WARP takes 512-row tiles: columns staged by TMA (cp.async.bulk + mbarrier, double buffered),
+//                        the bit-exact fp64 bin index, a counting sort of the tile by grid tile (one shared-memory atomic per
+//                        row for the rank, a warp scan for the segment starts), and a coalesced append of every segment to
+//                        that grid tile's bucket in global memory as 16-bit local indices (2 B/row), space reserved in
+//                        512-entry chunks.
+//   K2 k_tile_count      CTA (tile, slice) zeroes a private u32 histogram of the tile in shared memory (<= 192 KB), streams its
 //                        slice of the bucket with 128-bit loads, ATOMS.POPC.INC per entry, then flushes the non-zero cells with
 //                        one RED.ADD.64 each into the int64 grid.
-// L2 requests per row drop from 1.25 to ~0.4, HBM traffic rises from 8 to 12 B/row; exact integer counts, same grid layout.
-// Buckets are provisioned for 4x the uniform share; a segment that would overflow its bucket is applied with direct REDs
-// instead (degenerate distributions stay correct, just slower).
+// L2 requests per row drop from 1.25 to ~0.4, HBM traffic rises from 8 to ~13 B/row; exact integer counts, same grid layout.
+// Buckets are provisioned for 4x the uniform share; a (warp, tile) whose chunk request would overflow the bucket applies its
+// rows with direct REDs instead (degenerate distributions stay exact, just slower).
 #include <algorithm>
 
 #include "binby.cuh"
@@ -32,17 +34,15 @@ struct TileParams {
     unsigned cells;
     unsigned tile_cells;          // cells per grid tile (<= 49152, multiple of 8): part = idx / tile_cells, local = idx % tile_cells < 2^16
     unsigned long long magic;     // ceil(2^42 / tile_cells): part = (idx * magic) >> 42, exact for idx < 2^22
-    int nparts, pbits;
+    int nparts;
     unsigned short *buckets; // nparts * cap entries
     unsigned long long cap;
     unsigned *cursors; // nparts: entries reserved so far (may run past cap)
-    unsigned *limits;  // nparts: start of the first segment that straddled cap (0xFFFFFFFF if none) — valid entries end there
     unsigned long long *grid;
 };
 
 namespace {
 
-constexpr int kThreads = 256;
 constexpr int kRounds = 16;            // rows per lane per warp tile
 constexpr int kWarpTile = 32 * kRounds; // 512 rows sorted per warp at a time
 constexpr unsigned kMaxTileCells = 49152; // 192 KB of u32 counters in k_tile_count
@@ -530,9 +530,6 @@ int try_launch_tilecount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
     p.tile_cells = tile_cells;
     p.magic = ((1ull << 42) + tile_cells - 1) / tile_cells;
     p.nparts = nparts;
-    p.pbits = 0;
-    while ((1 << p.pbits) < nparts)
-        p.pbits++;
     p.grid = static_cast<unsigned long long *>(a.grid);
 
     const long long batch = std::min<long long>(bp.nrows, 1ll << 28);
@@ -553,7 +550,6 @@ int try_launch_tilecount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
         slot->scratch_cap = need;
     }
     p.cursors = static_cast<unsigned *>(slot->scratch);
-    p.limits = p.cursors + 512;
     p.buckets = reinterpret_cast<unsigned short *>(static_cast<char *>(slot->scratch) + 4096);
     p.cap = cap;
     cudaStream_t st = slot->stream;
@@ -567,7 +563,6 @@ int try_launch_tilecount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
         p.row0 = r0;
         p.nrows = std::min<long long>(batch, bp.nrows - r0);
         B200_CUDA(cudaMemsetAsync(p.cursors, 0, 2048, st));
-        B200_CUDA(cudaMemsetAsync(p.limits, 0xff, 2048, st));
         if (t == B200_F32)
             B200_CHECK(launch_partition<float>(bp.nb, ctx->sm_count, p.nrows, st, p));
         else

@@ -86,3 +86,35 @@ def shard_range(nrows, rank, world):
     base, rem = divmod(int(nrows), int(world))
     i1 = rank * base + min(rank, rem)
     return i1, i1 + base + (1 if rank < rem else 0)
+
+
+def union_key_sets(local_set, group=None, make_set=None):
+    """Groupby pass 1 across GPUs: every rank built an ordered set over its own row range; all-gather the
+    unique keys (<= 8 MB for 1e6 int64 keys), and let every rank rebuild the SAME set by inserting the per-rank key arrays in
+    rank order — so all ranks derive identical ordinals (first-seen order of the row-sharded frame) without further exchange.
+
+    `local_set` is anything with the ordered_set protocol (`key_array()`, `nan_count`, `null_count`, `null_index`, `nan_index`
+    and a constructor `type(local_set)(nmaps)` + `update(keys[, masks], start_index)`): the device set here, the oracle's
+    restatement in the CPU test.  Returns the union set (a new object of the same type)."""
+    import numpy as np
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    keys = np.asarray(local_set.key_array())
+    special = (int(local_set.nan_count > 0), int(local_set.null_count > 0), int(local_set.nan_index), int(local_set.null_index))
+    payload = (keys, special)
+    gathered = [None] * world
+    if world > 1:
+        dist.all_gather_object(gathered, payload, group=group)
+    else:
+        gathered[0] = payload
+    union = make_set() if make_set is not None else type(local_set)(getattr(local_set, "nmaps", 1))
+    for k, (has_nan, has_null, nan_i, null_i) in gathered:
+        if len(k) == 0:
+            continue
+        mask = None
+        if has_null:
+            mask = np.zeros(len(k), bool)
+            mask[null_i] = True
+        # NaN slots carry NaN in key_array(), so they re-enter as NaN keys; null slots need the mask
+        union.update(k, masks=mask, start_index=-1)
+    return union
