@@ -33,7 +33,7 @@ struct TileParams {
     long long row0, nrows; // batch
     unsigned cells;
     unsigned tile_cells;          // cells per grid tile (<= 49152, multiple of 8): part = idx / tile_cells, local = idx % tile_cells < 2^16
-    unsigned long long magic;     // ceil(2^42 / tile_cells): part = (idx * magic) >> 42, exact for idx < 2^22
+    unsigned magic, magic_shift;  // part = (idx * magic) >> magic_shift with 2^31 <= magic < 2^32: one IMAD.WIDE + one shift, exact for idx < 2^22
     int nparts;
     unsigned short *buckets; // nparts * cap entries
     unsigned long long cap;
@@ -103,7 +103,7 @@ __device__ __forceinline__ void tile_rank(const TileParams &p, long long tbase, 
             // rank inside (warp, grid tile): one shared-memory atomic with return per row.  MATCH.ANY + SHFL ranking kept the
             // ADU pipe 70 % busy and 7-bit ballot ranking the ALU pipe 60 % busy (profiles/r01_ncu_tilecount_*.txt)
             if (FULL || r0 + j < tend) {
-                const unsigned part = (unsigned)(((unsigned long long)idx * p.magic) >> 42);
+                const unsigned part = (unsigned)(((unsigned long long)idx * p.magic) >> p.magic_shift);
                 const unsigned slot = atomicAdd(seg + part, 1u);
                 packed[q * 4 + j] = (idx - part * p.tile_cells) | (part << 16) | (slot << 23); // local(16) | part(7) | slot(9)
             } else {
@@ -169,7 +169,7 @@ __device__ __forceinline__ void tile_rank_staged(const TileParams &p, const T *b
 #pragma unroll
             for (int d = 0; d < ND; d++)
                 idx += bin_index(c[d][j], p.vmin[d], p.scale[d], p.bins_d[d], p.bins[d]) * p.stride[d];
-            const unsigned part = (unsigned)(((unsigned long long)idx * p.magic) >> 42);
+            const unsigned part = (unsigned)(((unsigned long long)idx * p.magic) >> p.magic_shift);
             const unsigned slot = atomicAdd(seg + part, 1u);
             packed[q * 4 + j] = (idx - part * p.tile_cells) | (part << 16) | (slot << 23);
         }
@@ -340,11 +340,19 @@ __global__ void __launch_bounds__(WARPS * 32, TMA ? 2 : 4) k_tile_partition(cons
         }
         __syncwarp();
         // ---- 3. scatter the tile into the warp's stage, sorted by grid tile ----------------------------------------------
+        if (nvalid == kWarpTile) {
 #pragma unroll
-        for (int r = 0; r < kRounds; r++) {
-            const unsigned pk = packed[r];
-            if (nvalid == kWarpTile || pk != 0xFFFFFFFFu)
+            for (int r = 0; r < kRounds; r++) {
+                const unsigned pk = packed[r];
                 stage[seg[(pk >> 16) & 127u] + (pk >> 23)] = pk & 0x7FFFFFu;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kRounds; r++) {
+                const unsigned pk = packed[r];
+                if (pk != 0xFFFFFFFFu)
+                    stage[seg[(pk >> 16) & 127u] + (pk >> 23)] = pk & 0x7FFFFFu;
+            }
         }
         __syncwarp();
         // ---- 4. append every segment to its bucket (consecutive lanes -> consecutive 16-bit entries of one segment) -------
@@ -528,7 +536,15 @@ int try_launch_tilecount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
     }
     p.cells = (unsigned)cells;
     p.tile_cells = tile_cells;
-    p.magic = ((1ull << 42) + tile_cells - 1) / tile_cells;
+    {
+        // floor(n / d) == (n * M) >> k for every n < 2^22 when M = ceil(2^k / d) and n * (M*d - 2^k) < 2^k; with
+        // k = 31 + ceil(log2 d): M < 2^32 and (M*d - 2^k) < d <= 2^16, so n * d < 2^38 <= 2^k holds for d >= 128
+        int lg = 0;
+        while ((1u << lg) < tile_cells)
+            lg++;
+        p.magic_shift = 31 + lg;
+        p.magic = (unsigned)((((unsigned long long)1 << p.magic_shift) + tile_cells - 1) / tile_cells);
+    }
     p.nparts = nparts;
     p.grid = static_cast<unsigned long long *>(a.grid);
 
