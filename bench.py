@@ -283,6 +283,31 @@ def run_b200(args):
         "clocks": clocks,
     }
 
+    # ---- BASELINE.json configs[1] (df.sum(z, binby=[x,y], shape=1024) on the same rows), reported beside the headline -----
+    if rank == 0 and world == 1 and not args.no_cpu:
+        z = torch.empty(rows, dtype=torch.float32, device="cuda").normal_(generator=gen)
+        asum = superagg.AggSum_float32(grid, 1, 4)
+        asum.set_data(0, z, 0)
+
+        def sum_step():
+            asum.reset(0)
+            grid.bin(0, [asum], rows)
+        sum_step()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(3):
+            sum_step()
+        s1.record(stream)
+        ctx.sync(0)
+        torch.cuda.synchronize()
+        sms = s0.elapsed_time(s1) / 3
+        out["also"] = {"configs[1] df.sum(z, binby=[x,y], shape=1024), fp32, device-resident": {
+            "rows_per_s": rows / (sms * 1e-3), "ms_per_step": sms, "algorithmic_bytes_per_row": 12,
+            "achieved_gbs": 12 * rows / (sms * 1e-3) / 1e9, "frac": 12 * rows / (sms * 1e-3) / 1e9 / peak,
+            "kernel": "k_binby_fast<float,2,float> (one RED.ADD.F64 per row: L2-request bound, DESIGN.md section 4)"}}
+        del z, asum
+
     # ---- e2e: host buffers through the C ABI, H2D inside the timed region -------------------------------------------
     if not args.no_e2e:
         erows = int(args.e2e_rows)
