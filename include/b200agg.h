@@ -172,6 +172,12 @@ size_t b200_set_bytes(b200_set *set);
  */
 int b200_minmax(b200_ctx *ctx, int slot, int dtype, int byteswap, const void *data, const uint8_t *mask, int64_t nrows, int memspace, double *out);
 
+/* ---- host-chunk ingestion ---------------------------------------------- */
+/* Page-lock a host column once (cudaHostRegister) so that the per-chunk H2D copies of b200_bin(HOST) run at PCIe rate and
+ * truly asynchronously; the reference has no counterpart (its columns are mmapped/numpy memory read by the CPU in place). */
+int b200_host_register(const void *ptr, size_t bytes);
+int b200_host_unregister(const void *ptr);
+
 /* ---- test hook ------------------------------------------------------------------------------ */
 uint64_t b200_hash64(uint64_t x);
 

@@ -111,6 +111,8 @@ def lib():
             "b200_set_isin": (i32, [vp, i32, vp, i64, vp, i32, u32]),
             "b200_set_bytes": (sz, [vp]),
             "b200_minmax": (i32, [vp, i32, i32, i32, vp, vp, i64, i32, vp]),
+            "b200_host_register": (i32, [vp, sz]),
+            "b200_host_unregister": (i32, [vp]),
             "b200_hash64": (u64, [u64]),
         }
         for name, (res, args) in sig.items():
@@ -259,3 +261,24 @@ def mask_column(ar):
     elif a.dtype.itemsize != 1:
         a = a.astype(np.uint8)
     return column(a)
+
+
+class pinned:
+    """Context manager / handle that page-locks numpy columns for the lifetime of a computation (b200_host_register)."""
+
+    def __init__(self, *arrays):
+        self.arrays = [a for a in arrays if isinstance(a, np.ndarray) and a.size and a.flags.c_contiguous]
+        context()  # cudaHostRegister needs a CUDA context
+        for a in self.arrays:
+            check(lib().b200_host_register(a.ctypes.data, a.nbytes))
+
+    def release(self):
+        for a in self.arrays:
+            lib().b200_host_unregister(a.ctypes.data)
+        self.arrays = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.release()

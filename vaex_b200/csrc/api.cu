@@ -245,6 +245,30 @@ int b200_ctx_sync(b200_ctx *ctx, int slot) {
 
 int b200_ctx_device(const b200_ctx *ctx) { return ctx ? ctx->device : -1; }
 
+int b200_host_register(const void *ptr, size_t bytes) {
+    if (!ptr || !bytes) {
+        set_error("b200_host_register: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    cudaError_t e = cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return B200_OK;
+    }
+    B200_CUDA(e);
+    return B200_OK;
+}
+
+int b200_host_unregister(const void *ptr) {
+    cudaError_t e = cudaHostUnregister(const_cast<void *>(ptr));
+    if (e == cudaErrorHostMemoryNotRegistered) {
+        cudaGetLastError();
+        return B200_OK;
+    }
+    B200_CUDA(e);
+    return B200_OK;
+}
+
 int b200_ctx_stream(b200_ctx *ctx, int slot, void **stream_out) {
     if (!ctx || slot < 0 || slot >= ctx->nslots || !stream_out) {
         set_error("b200_ctx_stream: invalid argument");

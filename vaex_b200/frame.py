@@ -25,8 +25,10 @@ def _dtype_of(ar):
 
 
 class Frame:
-    def __init__(self, columns, nthreads=None, executor=None, categories=None):
+    def __init__(self, columns, nthreads=None, executor=None, categories=None, pin=False):
+        """pin=True page-locks the host (numpy) columns once so that chunk uploads run at PCIe rate (b200_host_register)."""
         self.columns = dict(columns)
+        self._pinned = _lib.pinned(*[v for v in self.columns.values() if isinstance(v, np.ndarray) and not np.ma.isMaskedArray(v)]) if pin else None
         self.executor = executor or execution.Executor(nthreads)
         self.categories = dict(categories or {})  # name -> (min_value, count): ordinal-coded columns (df.categorize)
         n = {len(v) for v in self.columns.values()}
