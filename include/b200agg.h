@@ -166,6 +166,10 @@ int b200_set_ordinal_dtype(b200_set *set);
 int b200_set_map_ordinal(b200_set *set, int slot, const void *keys, int64_t nrows, void *out, int memspace, uint32_t flags);
 int b200_set_isin(b200_set *set, int slot, const void *keys, int64_t nrows, uint8_t *out, int memspace, uint32_t flags);
 size_t b200_set_bytes(b200_set *set);
+/* counter_<T> (src/hash_primitives.hpp:344-433, value_counts / unique): an ordered set that also counts the occurrences of each
+ * key; `b200_set_counts` returns them in the order of b200_set_key_array (NaN / null slots hold their own counts). */
+int b200_counter_create(b200_ctx *ctx, int dtype, int nmaps, b200_set **out);
+int b200_set_counts(b200_set *set, int64_t *counts_out);
 
 /* ---- limits pre-pass ------------------------------------------------------------------------ */
 /* out[0] = min, out[1] = max over non-NaN, unmasked values, as double; out = {+inf,-inf} when empty.

@@ -110,6 +110,8 @@ def lib():
             "b200_set_map_ordinal": (i32, [vp, i32, vp, i64, vp, i32, u32]),
             "b200_set_isin": (i32, [vp, i32, vp, i64, vp, i32, u32]),
             "b200_set_bytes": (sz, [vp]),
+            "b200_counter_create": (i32, [vp, i32, i32, P(vp)]),
+            "b200_set_counts": (i32, [vp, vp]),
             "b200_minmax": (i32, [vp, i32, i32, i32, vp, vp, i64, i32, vp]),
             "b200_host_register": (i32, [vp, sz]),
             "b200_host_unregister": (i32, [vp]),

@@ -23,6 +23,9 @@ struct b200_set {
     int64_t limit = -1;
     b200::SetSlot *table = nullptr; // insert table: first = tag
     uint64_t cap = 0;
+    unsigned long long *counts = nullptr; // counter<T> mode (src/hash_primitives.hpp:344-433): occurrences per slot, parallel to `table`
+    bool counting = false;
+    bool hold_count_pass = false; // merge: keys are inserted first, the other set's counts are added afterwards
     unsigned long long *d_ctr = nullptr; // see CTR_*
     int64_t seq = 0;
     bool dirty = true;
@@ -40,7 +43,7 @@ struct b200_set {
 
 namespace b200 {
 
-enum { CTR_COUNT = 0, CTR_OVERFLOW, CTR_NAN_COUNT, CTR_NULL_COUNT, CTR_NAN_TAG, CTR_NULL_TAG, CTR_SENTINEL_TAG, CTR_CURSOR, CTR_N };
+enum { CTR_COUNT = 0, CTR_OVERFLOW, CTR_NAN_COUNT, CTR_NULL_COUNT, CTR_NAN_TAG, CTR_NULL_TAG, CTR_SENTINEL_TAG, CTR_CURSOR, CTR_SENTINEL_COUNT, CTR_N };
 
 namespace {
 
@@ -144,6 +147,51 @@ __global__ void __launch_bounds__(256) k_set_insert(SetSlot *table, unsigned lon
     }
 }
 
+// counter<T>::add_new / add_existing (src/hash_primitives.hpp:377-386): one occurrence per row.  Runs AFTER the insert pass of
+// the same rows succeeded, so every key is present and the pass is not repeated when the table grows.
+__global__ void __launch_bounds__(256) k_set_count(const SetSlot *table, unsigned long long mask, unsigned long long *counts, unsigned long long *ctr, int dtype,
+                                                   int isz, const void *keys, const uint8_t *masks, const unsigned long long *weights, long long nrows) {
+    unsigned long long n_sent = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += (long long)gridDim.x * blockDim.x) {
+        const uint64_t raw = load_raw1(keys, isz, i);
+        if ((masks && masks[i]) || raw_isnan(dtype, raw))
+            continue; // NaN / null occurrences are counted by k_set_insert
+        const unsigned long long w = weights ? weights[i] : 1ull;
+        const unsigned long long canon = key_canon(dtype, raw);
+        if (canon == SET_EMPTY) {
+            n_sent += w;
+            continue;
+        }
+        unsigned long long h = hash64(canon) & mask;
+        for (int step = 0; step < kMaxProbe; step++) {
+            const unsigned long long k = table[h].key;
+            if (k == canon) {
+                atomicAdd(counts + h, w);
+                break;
+            }
+            if (k == SET_EMPTY)
+                break;
+            h = (h + 1) & mask;
+        }
+    }
+    if (n_sent)
+        atomicAdd(ctr + CTR_SENTINEL_COUNT, n_sent);
+}
+
+// counts in ordinal order: slot -> ordinal through the finalized probe table
+__global__ void k_counts_gather(const SetSlot *table, unsigned long long cap, const unsigned long long *counts, const SetSlot *probe, unsigned long long pmask,
+                                unsigned long long *out) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = table[i].key;
+        if (k == SET_EMPTY)
+            continue;
+        unsigned long long h = hash64(k) & pmask;
+        while (probe[h].key != k)
+            h = (h + 1) & pmask;
+        out[probe[h].first] = counts[i];
+    }
+}
+
 __global__ void k_set_init(SetSlot *table, unsigned long long cap) {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (unsigned long long)gridDim.x * blockDim.x) {
         table[i].key = SET_EMPTY;
@@ -151,7 +199,8 @@ __global__ void k_set_init(SetSlot *table, unsigned long long cap) {
     }
 }
 
-__global__ void k_set_rehash(const SetSlot *old, unsigned long long old_cap, SetSlot *table, unsigned long long mask) {
+__global__ void k_set_rehash(const SetSlot *old, unsigned long long old_cap, SetSlot *table, unsigned long long mask, const unsigned long long *old_counts,
+                             unsigned long long *counts) {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < old_cap; i += (unsigned long long)gridDim.x * blockDim.x) {
         unsigned long long k = old[i].key;
         if (k == SET_EMPTY)
@@ -160,6 +209,8 @@ __global__ void k_set_rehash(const SetSlot *old, unsigned long long old_cap, Set
         while (atomicCAS(&table[h].key, SET_EMPTY, k) != SET_EMPTY)
             h = (h + 1) & mask;
         table[h].first = old[i].first;
+        if (counts)
+            counts[h] = old_counts[i];
     }
 }
 
@@ -283,6 +334,10 @@ inline int nblocks(unsigned long long n, int threads = 256) {
 int set_alloc_table(b200_set *s, uint64_t cap, cudaStream_t st) {
     B200_CUDA(cudaMalloc(&s->table, cap * sizeof(SetSlot)));
     s->cap = cap;
+    if (s->counting) {
+        B200_CUDA(cudaMalloc(&s->counts, cap * sizeof(unsigned long long)));
+        B200_CUDA(cudaMemsetAsync(s->counts, 0, cap * sizeof(unsigned long long), st));
+    }
     k_set_init<<<nblocks(cap), 256, 0, st>>>(s->table, cap);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
@@ -290,12 +345,15 @@ int set_alloc_table(b200_set *s, uint64_t cap, cudaStream_t st) {
 
 int set_grow(b200_set *s, cudaStream_t st) {
     SetSlot *old = s->table;
+    unsigned long long *old_counts = s->counts;
     uint64_t old_cap = s->cap;
     B200_CHECK(set_alloc_table(s, old_cap * 4, st));
-    k_set_rehash<<<nblocks(old_cap), 256, 0, st>>>(old, old_cap, s->table, s->cap - 1);
+    k_set_rehash<<<nblocks(old_cap), 256, 0, st>>>(old, old_cap, s->table, s->cap - 1, old_counts, s->counts);
     B200_CUDA(cudaGetLastError());
     B200_CUDA(cudaStreamSynchronize(st));
     B200_CUDA(cudaFree(old));
+    if (old_counts)
+        B200_CUDA(cudaFree(old_counts));
     return B200_OK;
 }
 
@@ -447,6 +505,9 @@ int set_insert_device(b200_set *s, cudaStream_t st, const void *d_keys, const ui
         redo = 0;
         row0 += n;
     }
+    if (s->counting && !s->hold_count_pass && !skip_keys && nrows)
+        k_set_count<<<nblocks((unsigned long long)nrows), 256, 0, st>>>(s->table, s->cap - 1, s->counts, s->d_ctr, s->dtype, isz, d_keys, d_masks, nullptr, nrows);
+    B200_CUDA(cudaGetLastError());
     s->dirty = true;
     return B200_OK;
 }
@@ -489,10 +550,53 @@ int b200_set_create(b200_ctx *ctx, int dtype, int nmaps, int64_t limit, b200_set
         return rc;
     }
     B200_CUDA(cudaMalloc(&s->d_ctr, sizeof(unsigned long long) * CTR_N));
-    unsigned long long init[CTR_N] = {0, 0, 0, 0, ~0ull, ~0ull, ~0ull, 0};
+    unsigned long long init[CTR_N] = {0, 0, 0, 0, ~0ull, ~0ull, ~0ull, 0, 0};
     B200_CUDA(cudaMemcpyAsync(s->d_ctr, init, sizeof init, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaStreamSynchronize(st));
     *out = s;
+    return B200_OK;
+}
+
+// counter_<T>(nmaps) (src/hash_primitives.cpp:36-43): an ordered set that also counts the occurrences of every key
+int b200_counter_create(b200_ctx *ctx, int dtype, int nmaps, b200_set **out) {
+    B200_CHECK(b200_set_create(ctx, dtype, nmaps, -1, out));
+    b200_set *s = *out;
+    s->counting = true;
+    cudaStream_t st = ctx->slots[0]->stream;
+    B200_CUDA(cudaMalloc(&s->counts, s->cap * sizeof(unsigned long long)));
+    B200_CUDA(cudaMemsetAsync(s->counts, 0, s->cap * sizeof(unsigned long long), st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+// counter::counts (src/hash_primitives.hpp:387-413) in the ordinal order of key_array(); the NaN / null slots hold their counts
+int b200_set_counts(b200_set *s, int64_t *out) {
+    if (!s || !out || !s->counting) {
+        set_error("b200_set_counts: not a counter");
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(s->ctx->device));
+    std::lock_guard<std::mutex> g(s->mu);
+    B200_CHECK(set_finalize(s));
+    cudaStream_t st = s->ctx->slots[0]->stream;
+    const size_t n = s->h_keys.size();
+    if (!n)
+        return B200_OK;
+    unsigned long long *d_out = nullptr;
+    B200_CUDA(cudaMalloc(&d_out, n * 8));
+    B200_CUDA(cudaMemsetAsync(d_out, 0, n * 8, st));
+    k_counts_gather<<<nblocks(s->cap), 256, 0, st>>>(s->table, s->cap, s->counts, s->probe, s->probe_cap - 1, d_out);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, st));
+    unsigned long long h[CTR_N];
+    B200_CHECK(read_ctr(s, st, h));
+    cudaFree(d_out);
+    if (s->nan_count > 0)
+        out[s->nan_value] = s->nan_count;
+    if (s->null_count > 0)
+        out[s->null_value] = s->null_count;
+    if (s->sentinel_ordinal >= 0)
+        out[s->sentinel_ordinal] = (int64_t)h[CTR_SENTINEL_COUNT];
     return B200_OK;
 }
 
@@ -501,6 +605,7 @@ int b200_set_destroy(b200_set *s) {
         return B200_OK;
     cudaSetDevice(s->ctx->device);
     cudaFree(s->table);
+    cudaFree(s->counts);
     cudaFree(s->probe);
     cudaFree(s->d_ctr);
     cudaFree(s->d_offsets);
@@ -620,15 +725,23 @@ int b200_set_merge(b200_set *s, b200_set *const *others, int nothers) {
     B200_CUDA(cudaSetDevice(s->ctx->device));
     for (int i = 0; i < nothers; i++) {
         b200_set *o = others[i];
-        std::vector<uint64_t> keys;
+        std::vector<uint64_t> keys, weights;
+        std::vector<int64_t> o_counts;
         int64_t o_nan, o_null;
+        if (s->counting && o->counting) { // counter::merge adds the other's counts (src/hash_primitives.hpp:414-432)
+            o_counts.resize(std::max<int64_t>(b200_set_count(o), 1));
+            B200_CHECK(b200_set_counts(o, o_counts.data()));
+        }
         {
             std::lock_guard<std::mutex> g(o->mu);
             B200_CHECK(set_finalize(o));
             keys.reserve(o->h_keys.size());
             for (size_t k = 0; k < o->h_keys.size(); k++)
-                if ((int64_t)k != o->nan_value && (int64_t)k != o->null_value)
+                if ((int64_t)k != o->nan_value && (int64_t)k != o->null_value) {
                     keys.push_back(o->h_keys[k]);
+                    if (!o_counts.empty())
+                        weights.push_back((uint64_t)o_counts[k]);
+                }
             o_nan = o->nan_count;
             o_null = o->null_count;
         }
@@ -640,11 +753,21 @@ int b200_set_merge(b200_set *s, b200_set *const *others, int nothers) {
         int saved = s->dtype;
         Stager stg{s->ctx, sl, B200_MEM_HOST};
         stg.plan(keys.data(), keys.size() * 8);
+        if (!weights.empty())
+            stg.plan(weights.data(), weights.size() * 8);
         B200_CHECK(stg.commit());
         // canonical patterns re-enter through a raw 64-bit view; key_canon(U64) is the identity and the shard hash is
         // evaluated from s->dtype at finalize, so only the column width differs.
         s->dtype = B200_U64;
+        s->hold_count_pass = true;
         int rc = keys.empty() ? B200_OK : set_insert_device(s, sl->stream, stg.dev(keys.data()), nullptr, (int64_t)keys.size(), false, false, -1);
+        s->hold_count_pass = false;
+        if (!rc && s->counting && !weights.empty()) {
+            k_set_count<<<nblocks(keys.size()), 256, 0, sl->stream>>>(s->table, s->cap - 1, s->counts, s->d_ctr, B200_U64, 8, stg.dev(keys.data()), nullptr,
+                                                                      static_cast<const unsigned long long *>(stg.dev(weights.data())), (long long)keys.size());
+            if (cudaGetLastError() != cudaSuccess)
+                rc = B200_ERR_CUDA;
+        }
         s->dtype = saved;
         B200_CHECK(rc);
         // nan/null: counts add up; a special first seen through a merge takes the next shard-0 ordinal

@@ -213,3 +213,60 @@ for _name in _lib.DTYPES:
     _cls.__module__ = __name__
     globals()["ordered_set_" + _name] = _cls
     copyreg.pickle(_cls, _pickle)
+
+
+class _Counter(_OrderedSet):
+    """``vaex.superutils.counter_<dtype>`` (src/hash_primitives.hpp:344-433, bound in src/hash_primitives.cpp:36-43): key ->
+    number of occurrences — what ``value_counts`` / ``unique`` run on (vaex/cpu.py:141-283).  Layout of ``keys()`` /
+    ``key_array()`` / ``counts()``: NaN first, then null, then the keys (the reference lists the keys in its container's
+    iteration order, which is unspecified; here they come in first-seen order)."""
+
+    def __init__(self, nmaps=1):
+        self._ctx = _lib.context()
+        self._h = C.c_void_p()
+        self.fingerprint = ""
+        self.sealed = False
+        self.nmaps = int(nmaps)
+        _lib.check(_lib.lib().b200_counter_create(self._ctx._h, self._code, self.nmaps, C.byref(self._h)))
+
+    def _order(self):
+        """ordinal positions reordered to the counter layout [nan][null][keys...]"""
+        n = len(self)
+        special = []
+        if self.nan_count:
+            special.append(_OrderedSet.nan_index.fget(self))
+        if self.null_count:
+            special.append(_OrderedSet.null_index.fget(self))
+        rest = [i for i in range(n) if i not in special]
+        return np.array(special + rest, dtype=np.int64)
+
+    nan_index = property(lambda self: 0)                                  # src/hash.hpp:289
+    null_index = property(lambda self: 1 if self.nan_count else 0)        # src/hash.hpp:290
+
+    def key_array(self):
+        return _OrderedSet.key_array(self)[self._order()] if len(self) else _OrderedSet.key_array(self)
+
+    def counts(self):
+        n = len(self)
+        out = np.zeros(n, np.int64)
+        if n:
+            _lib.check(_lib.lib().b200_set_counts(self._h, out.ctypes.data))
+            out = out[self._order()]
+        return out
+
+    def keys(self):
+        out = self.key_array().tolist()
+        if self.nan_count:
+            out[0] = math.nan
+        if self.null_count:
+            out[self.null_index] = None
+        return out
+
+    def map_ordinal(self, values):
+        raise AttributeError("counter has no map_ordinal")
+
+
+for _name in _lib.DTYPES:
+    _cls = type("counter_" + _name, (_Counter,), dict(_dtype=_name, _code=_lib.DTYPE_CODE[_name]))
+    _cls.__module__ = __name__
+    globals()["counter_" + _name] = _cls
