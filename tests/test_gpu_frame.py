@@ -172,3 +172,26 @@ def test_groupby_float_keys_nan_and_missing():
     out = gb.agg({"v": "sum"})
     got = {(None if np.ma.is_masked(k) else (float("nan") if k != k else float(k))): s for k, s in zip(out["k"], out["v_sum"])}
     assert got[1.5] == 3.0 and got[2.5] == 7.0 and got[9.0] == 7.0
+
+
+def test_value_counts_and_unique():
+    # tests/value_counts_test.py, tests/unique_test.py style: against numpy / collections
+    from vaex_b200.frame import Frame
+    rng = np.random.default_rng(10)
+    n = 50_000
+    k = rng.integers(0, 50, n).astype("i4")
+    f = np.ma.array(rng.integers(0, 5, n).astype("f8"), mask=rng.random(n) < 0.1)
+    f.data[::17] = np.nan
+    df = Frame(dict(k=k, f=f), executor=__import__("vaex_b200.execution", fromlist=["x"]).Executor(nthreads=2, chunk_size=7001))
+    keys, counts = df.value_counts("k")
+    u, c = np.unique(k, return_counts=True)
+    assert dict(zip(keys, counts.tolist())) == dict(zip(u.tolist(), c.tolist()))
+    assert list(counts) == sorted(counts, reverse=True)
+    assert sorted(df.unique("k")) == u.tolist()
+    keys, counts = df.value_counts("f")
+    valid = f.compressed()
+    assert counts[[i for i, q in enumerate(keys) if q is None][0]] == int(f.mask.sum())
+    assert counts[[i for i, q in enumerate(keys) if isinstance(q, float) and q != q][0]] == int(np.isnan(valid).sum())
+    keys, counts = df.value_counts("f", dropna=True)
+    u, c = np.unique(valid[~np.isnan(valid)], return_counts=True)
+    assert dict(zip(keys, counts.tolist())) == dict(zip(u.tolist(), c.tolist()))

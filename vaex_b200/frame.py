@@ -161,6 +161,34 @@ class Frame:
             self.columns[name] = col.double() if _is_device(col) else np.asarray(col).astype("float64")
         return name
 
+    # ---- value_counts / unique (counter<T>) ----------------------------------------------------------
+    def value_counts(self, expression, dropna=False, dropnan=False, dropmissing=False, ascending=False):
+        """df[expression].value_counts() (vaex/cpu.py:141-283 TaskPartValueCounts over counter_<dtype>): (keys, counts) sorted by
+        count; NaN / missing get their own entries unless dropped."""
+        from . import superutils
+        col = self.columns[expression]
+        dt = _dtype_of(col)
+        counter = getattr(superutils, "counter_" + np.dtype(dt).newbyteorder("=").name)(1)
+        chunk = self.executor.chunk_size_for(self.length) if not _is_device(col) else max(self.length, 1)
+        for i1 in range(0, self.length, chunk):
+            block = col[i1:i1 + chunk]
+            if not _is_device(block) and np.ma.isMaskedArray(block):
+                counter.update(np.ascontiguousarray(block.data), np.ma.getmaskarray(block))
+            else:
+                counter.update(block if _is_device(block) else np.ascontiguousarray(block))
+        keys, counts = counter.keys(), counter.counts()
+        keep = [i for i, k in enumerate(keys)
+                if not ((k is None and (dropna or dropmissing)) or (isinstance(k, float) and k != k and (dropna or dropnan)))]
+        keys, counts = [keys[i] for i in keep], counts[keep]
+        order = np.argsort(counts, kind="stable")
+        if not ascending:
+            order = order[::-1]
+        return [keys[i] for i in order], counts[order]
+
+    def unique(self, expression, dropna=False):
+        keys, _ = self.value_counts(expression, dropna=dropna)
+        return keys
+
     # ---- groupby ------------------------------------------------------------------------------------------------------
     def groupby(self, by, agg=None, sort=False, fused=True):
         gb = GroupBy(self, by, sort=sort, fused=fused)
