@@ -336,11 +336,18 @@ def run_b200(args):
 
         e2e_step()
         barrier()
+        sampler2 = ClockSampler(local)
+        sampler2.start()
         w0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             e2e_step()
         barrier()
         w = time.perf_counter() - w0
+        c2 = sampler2.result()
+        if c2.get("sm_mhz") is not None:  # the e2e steps are a timed region too: fold their clock samples in
+            both = sorted(sampler.samples + sampler2.samples)
+            out["clocks"] = {"sm_mhz": both[len(both) // 2], "sm_max_mhz": c2["sm_max_mhz"], "reasons": sorted(set(clocks["reasons"]) | set(c2["reasons"])),
+                             "samples": len(both), "windows": "device-resident steps + e2e steps"}
         if world > 1:
             t = torch.tensor([w], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
