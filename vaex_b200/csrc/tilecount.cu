@@ -569,11 +569,8 @@ int try_launch_tilecount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
     p.buckets = reinterpret_cast<unsigned short *>(static_cast<char *>(slot->scratch) + 4096);
     p.cap = cap;
     cudaStream_t st = slot->stream;
-    static bool attr_set = false;
-    if (!attr_set) {
-        B200_CUDA(cudaFuncSetAttribute(k_tile_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxTileCells * 4)));
-        attr_set = true;
-    }
+    // per device (function attributes live in the context): set on every call, it costs microseconds
+    B200_CUDA(cudaFuncSetAttribute(k_tile_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxTileCells * 4)));
     const int nslices = (int)((cap + kSlice - 1) / kSlice);
     for (long long r0 = 0; r0 < bp.nrows; r0 += batch) {
         p.row0 = r0;
