@@ -174,6 +174,45 @@ def test_interleaved_record_path_matches_oracle(oracle):
         assert np.allclose(got[k], want[k], rtol=RTOL, atol=1e-9)
 
 
+def test_region_sorted_path_matches_oracle(oracle, monkeypatch):
+    """grids larger than the L2 take the region-sorted path (csrc/tilesort.cu) from 2^24 rows on; here the thresholds are
+    lowered through its environment knobs so that every variant (64 / 128 regions, with and without a value column, fp32 /
+    fp64, ragged last tile, NaN keys and values, bucket overflow -> direct application) is checked against the oracle."""
+    monkeypatch.setenv("B200_TILESORT_FORCE", "1")
+    monkeypatch.setenv("B200_TILESORT_MIN_ROWS", "1000")
+    rng = np.random.default_rng(41)
+    n = 100_003
+    x, y = (rng.normal(0, 1, n).astype("f4") for _ in range(2))
+    v = rng.normal(0, 1, n)
+    x[::3331] = np.nan
+    v[::1777] = np.nan
+    b = [oracle.scalar(x, -3, 3, 300), oracle.scalar(y, -3, 3, 300)]
+    aggs = [oracle.agg("count", v), oracle.agg("sum", v), oracle.agg("sum_moment", v, moment=2), oracle.agg("count")]
+    want = oracle.binby(b, aggs, n)
+    for region_kb in (None, "32"):  # default: 45 regions; 32 KB budget: 90 regions (four per lane in the scan)
+        if region_kb:
+            monkeypatch.setenv("B200_TILESORT_REGION_KB", region_kb)
+        for device in (True, False):
+            got = b200_binby(b, aggs, n, device=device)
+            assert np.array_equal(want[0], got[0]) and np.array_equal(want[3], got[3])
+            for k in (1, 2):
+                assert np.allclose(got[k], want[k], rtol=RTOL, atol=1e-9)
+    monkeypatch.delenv("B200_TILESORT_REGION_KB")
+    # no value column, fp64 keys, 3-D
+    a, c, d = (rng.normal(0, 1, n) for _ in range(3))
+    b = [oracle.scalar(a, -3, 3, 40), oracle.scalar(c, -2, 3, 41), oracle.scalar(d, -3, 2, 42)]
+    assert np.array_equal(oracle.binby(b, [oracle.agg("count")], n)[0], b200_binby(b, [oracle.agg("count")], n, device=True)[0])
+    # one hot cell: its bucket overflows and the excess is applied directly
+    x = np.full(n, 0.5, "f4")
+    y = np.full(n, -0.25, "f4")
+    vf = rng.normal(0, 1, n).astype("f4")
+    b = [oracle.scalar(x, -3, 3, 300), oracle.scalar(y, -3, 3, 300)]
+    aggs = [oracle.agg("count", vf), oracle.agg("sum", vf)]
+    want, got = oracle.binby(b, aggs, n), b200_binby(b, aggs, n, device=True)
+    assert np.array_equal(want[0], got[0]) and int(got[0].sum()) == n
+    assert np.allclose(got[1], want[1], rtol=RTOL, atol=1e-9)
+
+
 def test_large_properties():
     """Full-size style properties that need no oracle: conservation of rows, chunk-sum consistency, idempotent merge."""
     import torch

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200agg.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "binby.cu", "fast.cu", "first.cu", "hashset.cu", "tilecount.cu"]
+SOURCES = ["api.cu", "binby.cu", "fast.cu", "first.cu", "hashset.cu", "tilecount.cu", "tilesort.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 

@@ -62,6 +62,26 @@ struct FirstParams {
     uint8_t *cell_masked;
 };
 
+// specialised float-binner paths (fast.cu, tilesort.cu)
+struct FastParams {
+    const void *x[3];
+    double vmin[3], scale[3], bins_d[3];
+    unsigned bins[3];
+    unsigned stride[3];
+    long long nrows;
+    unsigned cells;
+    const void *v;                      // value column or null
+    unsigned long long *count_star;     // nullable grids (global)
+    unsigned long long *vcount;
+    double *vsum;
+    double *vm2;
+    int smem_copies;                    // > 0: privatise in shared memory (u32 counts, f64 sums)
+    unsigned long long *aos;            // non-null: accumulate into interleaved 32-byte records {count*, count(v), sum, sum2}
+};
+
+// tilesort.cu: rows sorted by grid region first, so that the scatter works on an L2-resident part of the grids
+int try_launch_tilesort(b200_ctx *ctx, Slot *slot, const FastParams &p, int xdtype, int nd, int vdtype, bool *taken);
+
 int launch_binby(b200_ctx *ctx, Slot *slot, const BinParams &p, bool vec);
 int launch_first(b200_ctx *ctx, cudaStream_t stream, const FirstParams &p, bool vec);
 int launch_fill(cudaStream_t stream, void *ptr, int cell_dtype, uint64_t cells, uint64_t bits);

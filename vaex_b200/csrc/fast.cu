@@ -18,21 +18,6 @@
 
 namespace b200 {
 
-struct FastParams {
-    const void *x[3];
-    double vmin[3], scale[3], bins_d[3];
-    unsigned bins[3];
-    unsigned stride[3];
-    long long nrows;
-    unsigned cells;
-    const void *v;                      // value column or null
-    unsigned long long *count_star;     // nullable grids (global)
-    unsigned long long *vcount;
-    double *vsum;
-    double *vm2;
-    int smem_copies;                    // > 0: privatise in shared memory (u32 counts, f64 sums)
-    unsigned long long *aos;            // non-null: accumulate into interleaved 32-byte records {count*, count(v), sum, sum2}
-};
 
 namespace {
 
@@ -363,6 +348,15 @@ int try_launch_fast(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool vec, bo
         smem = copy * p.smem_copies;
     }
     const int naggs = (p.count_star != nullptr) + (p.vcount != nullptr) + (p.vsum != nullptr) + (p.vm2 != nullptr);
+    if (!smem && ((size_t)naggs * 8 * bp.cells > (100u << 20) || getenv("B200_TILESORT_FORCE"))) {
+        // accumulators larger than the L2: sort the rows by grid region first (tilesort.cu), when the input is big enough to pay for it
+        bool sorted = false;
+        B200_CHECK(try_launch_tilesort(ctx, slot, p, t, bp.nb, vdtype, &sorted));
+        if (sorted) {
+            *taken = true;
+            return B200_OK;
+        }
+    }
     static const bool aos_off = getenv("B200_DISABLE_AOS") && atoi(getenv("B200_DISABLE_AOS")) != 0;
     if (!smem && !aos_off && naggs >= 2 && (size_t)naggs * 8 * bp.cells > (100u << 20) && (unsigned long long)bp.nrows >= 8ull * bp.cells) {
         const size_t need = (size_t)bp.cells * 32;
