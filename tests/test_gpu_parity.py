@@ -157,9 +157,9 @@ def test_tile_partitioned_count_matches_oracle(oracle):
     assert np.array_equal(oracle.binby(b, [oracle.agg("count")], n)[0], got) and int(got.sum()) == n
 
 
-def test_interleaved_record_path_matches_oracle(oracle):
-    """mean+std primitives (count, sum, sum^2) on a grid larger than the L2 with many rows per cell take the interleaved
-    32-byte-record accumulation (csrc/fast.cu, k_aos_fold): counts bit-exact, sums within the 1e-6 tolerance."""
+def test_grid_larger_than_l2_matches_oracle(oracle):
+    """mean+std primitives (count, sum, sum^2) on a grid larger than the L2 at full thresholds (38M rows >= 2^24, 112 MB of
+    accumulators): the region-sorted path of csrc/tilesort.cu.  Counts bit-exact, sums within the 1e-6 tolerance."""
     rng = np.random.default_rng(31)
     n = 38_000_000
     x, y, z = (rng.normal(0, 1, n).astype("f4") for _ in range(3))

@@ -76,7 +76,6 @@ struct FastParams {
     double *vsum;
     double *vm2;
     int smem_copies;                    // > 0: privatise in shared memory (u32 counts, f64 sums)
-    unsigned long long *aos;            // non-null: accumulate into interleaved 32-byte records {count*, count(v), sum, sum2}
 };
 
 // tilesort.cu: rows sorted by grid region first, so that the scatter works on an L2-resident part of the grids

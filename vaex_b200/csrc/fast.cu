@@ -67,25 +67,6 @@ struct Vec<double> {
 template <typename TV, bool SMEM>
 __device__ __forceinline__ void scatter(const FastParams &p, unsigned idx, bool has_v, TV vraw, unsigned *s_count, unsigned *s_vcount, double *s_vsum,
                                         double *s_vm2) {
-    if (!SMEM && p.aos) {
-        // grids larger than the L2: all aggregates of a cell live in ONE 32-byte sector, so a row that misses the L2 costs one
-        // sector fill + write-back instead of one per aggregator (k_aos_fold adds the records into the real grids afterwards)
-        unsigned long long *rec = p.aos + 4ull * idx;
-        if (p.count_star)
-            atomicAdd(rec, 1ull);
-        if (has_v) {
-            const double v = widen<TV>(vraw);
-            if (v == v) {
-                if (p.vcount)
-                    atomicAdd(rec + 1, 1ull);
-                if (p.vsum)
-                    atomicAdd(reinterpret_cast<double *>(rec + 2), v);
-                if (p.vm2)
-                    atomicAdd(reinterpret_cast<double *>(rec + 3), v * v);
-            }
-        }
-        return;
-    }
     if (p.count_star) {
         if (SMEM)
             atomicAdd(s_count + idx, 1u);
@@ -232,20 +213,6 @@ __global__ void __launch_bounds__(kThreads) k_binby_fast(const __grid_constant__
     }
 }
 
-__global__ void k_aos_fold(const unsigned long long *aos, unsigned cells, unsigned long long *count_star, unsigned long long *vcount, double *vsum, double *vm2) {
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += gridDim.x * blockDim.x) {
-        const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(aos + 4ull * i), b = *reinterpret_cast<const ulonglong2 *>(aos + 4ull * i + 2);
-        if (count_star && a.x)
-            atomicAdd(count_star + i, a.x);
-        if (vcount && a.y)
-            atomicAdd(vcount + i, a.y);
-        if (vsum && b.x)
-            atomicAdd(vsum + i, __longlong_as_double((long long)b.x));
-        if (vm2 && b.y)
-            atomicAdd(vm2 + i, __longlong_as_double((long long)b.y));
-    }
-}
-
 template <typename T, int ND, typename TV, bool HASV>
 int launch3(b200_ctx *ctx, cudaStream_t stream, const FastParams &p, size_t smem) {
     auto go = [&](auto kern) -> int {
@@ -357,32 +324,8 @@ int try_launch_fast(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool vec, bo
             return B200_OK;
         }
     }
-    static const bool aos_off = getenv("B200_DISABLE_AOS") && atoi(getenv("B200_DISABLE_AOS")) != 0;
-    if (!smem && !aos_off && naggs >= 2 && (size_t)naggs * 8 * bp.cells > (100u << 20) && (unsigned long long)bp.nrows >= 8ull * bp.cells) {
-        const size_t need = (size_t)bp.cells * 32;
-        if (slot->scratch_cap < need) {
-            if (slot->scratch) {
-                B200_CUDA(cudaStreamSynchronize(stream));
-                B200_CUDA(cudaFree(slot->scratch));
-                slot->scratch = nullptr;
-                slot->scratch_cap = 0;
-            }
-            if (cudaMalloc(&slot->scratch, need) == cudaSuccess)
-                slot->scratch_cap = need;
-            else
-                cudaGetLastError();
-        }
-        if (slot->scratch_cap >= need) {
-            p.aos = static_cast<unsigned long long *>(slot->scratch);
-            B200_CUDA(cudaMemsetAsync(p.aos, 0, need, stream));
-        }
-    }
     *taken = true;
     int rc = t == B200_F32 ? launch1<float>(ctx, stream, p, bp.nb, vdtype, smem) : launch1<double>(ctx, stream, p, bp.nb, vdtype, smem);
-    if (rc == B200_OK && p.aos) {
-        k_aos_fold<<<ctx->sm_count * 8, 256, 0, stream>>>(p.aos, p.cells, p.count_star, p.vcount, p.vsum, p.vm2);
-        B200_CUDA(cudaGetLastError());
-    }
     return rc;
 }
 

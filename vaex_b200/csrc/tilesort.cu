@@ -1,9 +1,9 @@
 // tilesort.cu — binned count/sum/sum-of-squares over grids that do not fit in the L2 (config C3: 256^3 cells x 3 aggregators
 // = 417 MB of accumulators).
 //
-// With direct scatter every row touches up to three random 32-byte sectors of HBM (fill + write-back): the AoS variant in
-// fast.cu already packs them into one sector and still runs at ~1.5 TB/s of random sector traffic (43 ms per 1e9 rows,
-// profiles/r01_bench_configs.txt).  Here the rows of a batch are first SORTED BY GRID REGION (k_sort_partition: the same
+// With direct scatter every row touches up to three random 32-byte sectors of HBM (fill + write-back).  Packing the three
+// accumulators of a cell into one 32-byte record (the round's earlier "interleaved record" variant) brought that to one sector
+// and still ran at ~1.5 TB/s of random sector traffic: 43.6 ms per 1e9 rows (profiles/r01_bench_configs.txt).  Here the rows of a batch are first SORTED BY GRID REGION (k_sort_partition: the same
 // warp-autonomous counting sort as tilecount.cu, carrying {cell index u32, value f64} = 12 bytes per row), and the regions are
 // then applied one after another (k_sort_apply) — the part of the grids a region covers is <= 32 MB and stays in the 126 MB
 // L2, so the REDs never go to HBM and the pass is bound by the L2 request rate (~98 REDs/clk, profiles/r01_microbench.txt)
@@ -68,6 +68,10 @@ __device__ __forceinline__ void load4<double>(const void *p, long long i, double
     out[2] = __longlong_as_double(((long long)b.y << 32) | b.x), out[3] = __longlong_as_double(((long long)b.w << 32) | b.z);
 }
 
+__device__ __forceinline__ void l2_prefetch(const void *p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 template <bool HASV>
 __device__ __forceinline__ void apply_row(const FastParams &f, unsigned idx, double v) {
     if (f.count_star)
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_sort_partition(const __grid_
     }
     __syncwarp();
 
-    const long long ntiles = (p.nrows + kWarpTile - 1) / kWarpTile;
+    const long long ntiles = (p.nrows + kWarpTile - 1) / kWarpTile, nfull = p.nrows / kWarpTile;
     const long long wglobal = (long long)blockIdx.x * kWarps + warp, wtotal = (long long)gridDim.x * kWarps;
     for (long long tile = wglobal; tile < ntiles; tile += wtotal) {
         const long long tbase = p.row0 + tile * kWarpTile;
@@ -160,6 +164,17 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_sort_partition(const __grid_
                 if (HASV)
                     vals[qd * 4 + j] = vv[j];
             }
+        }
+        if (lane == 0 && tile + wtotal < nfull) {
+            // pull the NEXT tile's columns into the L2 while this one is sorted (not earlier: ~70 MB stream through the L2 per tile time, a line
+            // prefetched a whole tile ahead is gone again before it is used): the next loads then wait for an L2 hit instead of
+            // HBM (the kernel was 59 % stalled on them with 16 warps per SM, profiles/r01_ncu_tilesort.txt)
+            const long long nb = tbase + wtotal * kWarpTile;
+#pragma unroll
+            for (int d = 0; d < ND; d++)
+                l2_prefetch(static_cast<const T *>(f.x[d]) + nb, kWarpTile * sizeof(T));
+            if (HASV)
+                l2_prefetch(static_cast<const TV *>(f.v) + nb, kWarpTile * sizeof(TV));
         }
         __syncwarp();
         // ---- 2. exclusive scan of the per-region counts; place each segment in the warp's current chunk --------------------
@@ -346,7 +361,7 @@ int try_launch_tilesort(b200_ctx *ctx, Slot *slot, const FastParams &fp, int xdt
         const char *e = getenv(name);
         return e && *e ? atoll(e) : dflt;
     };
-    if (env_ll("B200_DISABLE_TILESORT", 0) || fp.nrows < env_ll("B200_TILESORT_MIN_ROWS", 1ll << 24) || fp.smem_copies || fp.aos)
+    if (env_ll("B200_DISABLE_TILESORT", 0) || fp.nrows < env_ll("B200_TILESORT_MIN_ROWS", 1ll << 24) || fp.smem_copies)
         return B200_OK;
     const unsigned long long region_bytes = (unsigned long long)env_ll("B200_TILESORT_REGION_KB", 32 << 10) << 10;
     const int naggs = (fp.count_star != nullptr) + (fp.vcount != nullptr) + (fp.vsum != nullptr) + (fp.vm2 != nullptr);
