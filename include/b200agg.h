@@ -75,7 +75,9 @@ typedef enum {
     B200_AGG_FIRST, B200_AGG_LAST
 } b200_agg_op;
 
-typedef enum { B200_MEM_HOST = 0, B200_MEM_DEVICE = 1 } b200_memspace;
+/* where the column pointers of a call live.  MIXED: every pointer is classified on its own (cudaPointerGetAttributes);
+   host columns are staged, device columns are used in place — e.g. device-computed group codes next to host value columns */
+typedef enum { B200_MEM_HOST = 0, B200_MEM_DEVICE = 1, B200_MEM_MIXED = 2 } b200_memspace;
 
 /* flags for b200_bin / b200_set_update */
 #define B200_FLAG_ASYNC_HOST 1u /* host buffers stay valid until b200_ctx_sync(slot): do not wait for the H2D copies */
@@ -166,6 +168,13 @@ int b200_set_ordinal_dtype(b200_set *set);
 int b200_set_map_ordinal(b200_set *set, int slot, const void *keys, int64_t nrows, void *out, int memspace, uint32_t flags);
 int b200_set_isin(b200_set *set, int slot, const void *keys, int64_t nrows, uint8_t *out, int memspace, uint32_t flags);
 size_t b200_set_bytes(b200_set *set);
+/* Sparse multi-key groupby (vaex/groupby.py:526-584 `_combine`: `sum_k _ordinal_values(key_k) * cumulative_counts[k+1]`,
+   vaex/functions.py:2454-2463): per row, the ordinal of every key column in its own set (null rows -> the set's null ordinal,
+   NaN -> its NaN ordinal) fused into ONE int64 code = sum_k ordinal_k * multipliers[k]; -1 when a key is in none of the
+   sets.  `masks[k]` may be NULL; `out` holds nrows int64 in the call's memspace. */
+#define B200_MAX_COMBINE 8
+int b200_set_combine(b200_ctx *ctx, int slot, int nkeys, b200_set *const *sets, const void *const *keys, const uint8_t *const *masks,
+                     const int64_t *multipliers, int64_t nrows, int64_t *out, int memspace, uint32_t flags);
 /* counter_<T> (src/hash_primitives.hpp:344-433, value_counts / unique): an ordered set that also counts the occurrences of each
  * key; `b200_set_counts` returns them in the order of b200_set_key_array (NaN / null slots hold their own counts). */
 int b200_counter_create(b200_ctx *ctx, int dtype, int nmaps, b200_set **out);

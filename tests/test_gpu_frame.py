@@ -195,3 +195,75 @@ def test_value_counts_and_unique():
     keys, counts = df.value_counts("f", dropna=True)
     u, c = np.unique(valid[~np.isnan(valid)], return_counts=True)
     assert dict(zip(keys, counts.tolist())) == dict(zip(u.tolist(), c.tolist()))
+
+
+@pytest.mark.parametrize("combine", [True, False])
+def test_groupby_with_missing_combine(combine):
+    # tests/groupby_test.py:334-343 (assume_sparse True / False): two keys, nulls sort last
+    from vaex_b200.frame import Frame
+    g1 = np.ma.array([0, 0, 1, 1, 1, 99, 99, 2], mask=[0, 0, 0, 0, 0, 1, 1, 0], dtype="i8")
+    g2 = np.array([0, 1, 0, 1, 1, 0, 1, 0], dtype="i8")
+    df = Frame(dict(g1=g1, g2=g2))
+    out = df.groupby(["g1", "g2"], agg=[__import__("vaex_b200.agg", fromlist=["x"]).count()], sort=True, combine=combine)
+    assert out["g1"].tolist() == [0, 0, 1, 1, 2, None, None]
+    assert out["g2"].tolist() == [0, 1, 0, 1, 0, 0, 1]
+    assert out["count"].tolist() == [1, 1, 1, 2, 1, 1, 1]
+
+
+@pytest.mark.parametrize("device", [False, True])
+@pytest.mark.parametrize("sort", [False, True])
+def test_groupby_sparse_combined_matches_numpy(device, sort, oracle):
+    """vaex/groupby.py:526-584 (_combine): 3000 x 2000 x 3 possible key combinations, 200k rows -> 'auto' combines (occupancy
+    < 10 rows per cell); sums / counts per distinct (k1, k2, k3) against numpy, host chunks and device-resident columns."""
+    import torch
+    from vaex_b200.execution import Executor
+    from vaex_b200.frame import Frame
+    rng = np.random.default_rng(23)
+    n = 200_000
+    k1 = rng.integers(0, 3000, n).astype("i8") * 1000 + 7
+    k2 = rng.integers(0, 2000, n).astype("f8") * 0.25
+    k2[rng.random(n) < 0.01] = np.nan
+    k3 = rng.integers(0, 3, n).astype("i4")
+    v = rng.normal(0, 1, n)
+    cols = dict(k1=k1, k2=k2, k3=k3, v=v)
+    if device:
+        cols = {k: torch.from_numpy(a).cuda() for k, a in cols.items()}
+    df = Frame(cols, executor=Executor(nthreads=3, chunk_size=33_333))
+    gb = df.groupby(["k1", "k2", "k3"], sort=sort, combine="auto")
+    assert gb.combined is not None
+    out = gb.agg({"v": ["sum", "count"]})
+    # numpy: distinct rows of (k1, k2-with-NaN-as-one-value, k3)
+    k2key = np.where(np.isnan(k2), -1.0, k2)
+    rec = np.rec.fromarrays([k1, k2key, k3])
+    uniq, inv = np.unique(rec, return_inverse=True)
+    want_sum = np.bincount(inv, weights=v)
+    want_cnt = np.bincount(inv)
+    got_k2 = np.where(np.isnan(np.asarray(out["k2"], dtype="f8")), -1.0, np.asarray(out["k2"], dtype="f8"))
+    got = np.rec.fromarrays([np.asarray(out["k1"]), got_k2, np.asarray(out["k3"])])
+    assert len(got) == len(uniq)
+    order = np.argsort(got)
+    assert np.array_equal(got[order], uniq)
+    np.testing.assert_array_equal(out["count"][order], want_cnt)
+    np.testing.assert_array_equal(out["v_count"][order], want_cnt)
+    np.testing.assert_allclose(out["v_sum"][order], want_sum, rtol=1e-9, atol=1e-9)
+    if sort:  # lexicographic by (k1, k2, k3), NaN after the numbers
+        nan_last = np.where(np.isnan(np.asarray(out["k2"], dtype="f8")), np.inf, np.asarray(out["k2"], dtype="f8"))
+        lex = np.lexsort((np.asarray(out["k3"]), nan_last, np.asarray(out["k1"])))
+        assert np.array_equal(lex, np.arange(len(lex)))
+    else:
+        # the sequential reference's order: ordinals of the combined codes in an ordered_set with 7 shards (vaex/cpu.py:317),
+        # restated with the oracle's ordered sets end to end
+        keys = [k1, k2, k3]
+        sets = [oracle.OrderedSet(k.dtype.name, 7) for k in keys]
+        for s_, k in zip(sets, keys):
+            s_.update(k, None, -1, False)
+        mult = [len(sets[1]) * len(sets[2]), len(sets[2]), 1]
+        codes = sum(s_.map_ordinal(k).astype("i8") * m for s_, k, m in zip(sets, keys, mult))
+        cs = oracle.OrderedSet("int64", 7)
+        cs.update(codes, None, -1, False)
+        want_codes = cs.key_array()
+        o1, rest = want_codes // mult[0], want_codes % mult[0]
+        o2, o3 = rest // mult[1], rest % mult[1]
+        assert np.array_equal(np.asarray(out["k1"]), sets[0].key_array()[o1])
+        assert np.array_equal(np.asarray(out["k2"], dtype="f8"), sets[1].key_array()[o2], equal_nan=True)
+        assert np.array_equal(np.asarray(out["k3"]), sets[2].key_array()[o3])

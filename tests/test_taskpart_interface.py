@@ -81,3 +81,17 @@ def test_plugin_install_fails_cleanly_without_vaex():
     except Exception:
         with pytest.raises(Exception):
             taskpart.install_into_vaex()
+
+
+def test_combined_codes_decode_matches_reference_div_mod_chain():
+    """GrouperCombined recovers the parents' ordinals with a div/mod chain over cumulative_counts[1:]
+    (vaex/groupby.py:352-358; the docstring example there: N = 10 and 4 -> cumulative counts [40, 4, 1])."""
+    from vaex_b200.hash import CombinedCodes
+    cc = CombinedCodes([np.zeros(3), np.zeros(3)], [None, None], [4, 1])
+    o0, o1 = np.array([0, 9, 3, 7]), np.array([3, 0, 2, 1])
+    d0, d1 = cc.decode(o0 * 4 + o1)
+    assert d0.tolist() == o0.tolist() and d1.tolist() == o1.tolist()
+    cc = CombinedCodes([np.zeros(1)] * 3, [None] * 3, [35, 7, 1])  # N = (_, 5, 7)
+    d = cc.decode(np.array([2 * 35 + 4 * 7 + 6]))
+    assert [int(x[0]) for x in d] == [2, 4, 6]
+    assert len(cc) == 1 and cc.dtype == np.int64 and cc.device_virtual

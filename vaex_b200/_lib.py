@@ -24,7 +24,7 @@ DTYPE_CODE = {n: i for i, n in enumerate(DTYPES)}
 F64, F32, I64, I32, I16, I8, U64, U32, U16, U8, BOOL = range(11)
 BINNER_SCALAR, BINNER_ORDINAL, BINNER_HASH = 0, 1, 2
 AGG_COUNT, AGG_SUM, AGG_SUM_MOMENT, AGG_MIN, AGG_MAX, AGG_FIRST, AGG_LAST = range(7)
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_MIXED = 0, 1, 2
 FLAG_ASYNC_HOST = 1
 ERR_NODATA = -3
 
@@ -109,6 +109,7 @@ def lib():
             "b200_set_ordinal_dtype": (i32, [vp]),
             "b200_set_map_ordinal": (i32, [vp, i32, vp, i64, vp, i32, u32]),
             "b200_set_isin": (i32, [vp, i32, vp, i64, vp, i32, u32]),
+            "b200_set_combine": (i32, [vp, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i64, vp, i32, u32]),
             "b200_set_bytes": (sz, [vp]),
             "b200_counter_create": (i32, [vp, i32, i32, P(vp)]),
             "b200_set_counts": (i32, [vp, vp]),

@@ -42,8 +42,19 @@ int slot_reserve(b200_ctx *ctx, Slot *s, size_t bytes) {
     return B200_OK;
 }
 
+bool is_device_pointer(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
 void Stager::plan(const void *p, size_t bytes) {
     if (!p || memspace == B200_MEM_DEVICE)
+        return;
+    if (memspace == B200_MEM_MIXED && is_device_pointer(p))
         return;
     for (auto &e : entries)
         if (e.host == p) { // the same column used twice (e.g. binby x and sum x) is copied once
@@ -76,7 +87,7 @@ const void *Stager::dev(const void *p) const {
     for (auto &e : entries)
         if (e.host == p)
             return e.dev;
-    return nullptr;
+    return memspace == B200_MEM_MIXED ? p : nullptr; // MIXED: not planned == already on the device
 }
 
 // identity element of an aggregator's device cell
@@ -731,7 +742,7 @@ int b200_bin(b200_ctx *ctx, int slot, const b200_binner *binners, int nbinners, 
     }
     B200_CHECK(flush());
 
-    if (memspace == B200_MEM_HOST && !(flags & B200_FLAG_ASYNC_HOST)) {
+    if (memspace != B200_MEM_DEVICE && !(flags & B200_FLAG_ASYNC_HOST)) {
         // the caller's buffers are only valid during the call (vaex/cpu.py:708-710).  Callers that keep them alive pass
         // B200_FLAG_ASYNC_HOST and overlap the next chunk's H2D copy (another slot) with this slot's kernel.
         B200_CUDA(cudaStreamSynchronize(st));

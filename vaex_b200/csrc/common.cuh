@@ -126,6 +126,7 @@ struct Stager {
 };
 
 int slot_reserve(b200_ctx *ctx, Slot *s, size_t bytes);
+bool is_device_pointer(const void *p);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -304,6 +304,36 @@ __global__ void __launch_bounds__(256) k_set_map(const SetSlot *probe, unsigned 
     }
 }
 
+// fused ordinal lookup of up to B200_MAX_COMBINE key columns -> one int64 group code (vaex/groupby.py:526-584)
+struct CombineParams {
+    int nkeys;
+    const SetSlot *probe[B200_MAX_COMBINE];
+    unsigned long long mask[B200_MAX_COMBINE];
+    long long sentinel[B200_MAX_COMBINE], nan_ord[B200_MAX_COMBINE], null_ord[B200_MAX_COMBINE], mult[B200_MAX_COMBINE];
+    int dtype[B200_MAX_COMBINE], isz[B200_MAX_COMBINE];
+    const void *keys[B200_MAX_COMBINE];
+    const uint8_t *masks[B200_MAX_COMBINE];
+};
+
+__global__ void __launch_bounds__(256) k_set_combine(const __grid_constant__ CombineParams p, long long nrows, long long *out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += (long long)gridDim.x * blockDim.x) {
+        long long acc = 0;
+        bool missing = false;
+        for (int k = 0; k < p.nkeys; k++) {
+            long long o;
+            if (p.masks[k] && p.masks[k][i]) {
+                o = p.null_ord[k];
+            } else {
+                const uint64_t raw = load_raw1(p.keys[k], p.isz[k], i);
+                o = raw_isnan(p.dtype[k], raw) ? p.nan_ord[k] : probe_lookup(p.probe[k], p.mask[k], p.sentinel[k], key_canon(p.dtype[k], raw));
+            }
+            missing |= o < 0;
+            acc += o * p.mult[k];
+        }
+        out[i] = missing ? -1 : acc;
+    }
+}
+
 // update(..., return_values=True): per row the shard-local ordinal and the shard (src/hash_primitives.hpp:139-176)
 __global__ void __launch_bounds__(256) k_set_values(const SetSlot *probe, unsigned long long mask, long long sentinel_ordinal, long long nan_ordinal,
                                                     long long null_ordinal, int dtype, int isz, int nmaps, const long long *offsets, const void *keys,
@@ -876,13 +906,14 @@ static int set_map_common(b200_set *s, int slot, const void *keys, int64_t nrows
     stg.plan(keys, (size_t)nrows * isz);
     B200_CHECK(stg.commit());
     void *d_out = out;
-    if (memspace == B200_MEM_HOST)
+    const bool out_host = memspace == B200_MEM_HOST || (memspace == B200_MEM_MIXED && !is_device_pointer(out));
+    if (out_host)
         B200_CUDA(cudaMalloc(&d_out, nrows * osz));
     k_set_map<<<nblocks((unsigned long long)nrows), 256, 0, sl->stream>>>(s->probe, s->probe_cap - 1, s->sentinel_ordinal,
                                                                         s->nan_count > 0 ? s->nan_value : -1, s->dtype, (int)isz, stg.dev(keys), nrows, d_out,
                                                                         out_isz);
     B200_CUDA(cudaGetLastError());
-    if (memspace == B200_MEM_HOST) {
+    if (out_host) {
         B200_CUDA(cudaMemcpyAsync(out, d_out, nrows * osz, cudaMemcpyDeviceToHost, sl->stream));
         B200_CUDA(cudaStreamSynchronize(sl->stream));
         cudaFree(d_out);
@@ -900,6 +931,65 @@ int b200_set_map_ordinal(b200_set *s, int slot, const void *keys, int64_t nrows,
 int b200_set_isin(b200_set *s, int slot, const void *keys, int64_t nrows, uint8_t *out, int memspace, uint32_t flags) {
     (void)flags;
     return set_map_common(s, slot, keys, nrows, out, 0, memspace);
+}
+
+int b200_set_combine(b200_ctx *ctx, int slot, int nkeys, b200_set *const *sets, const void *const *keys, const uint8_t *const *masks,
+                     const int64_t *multipliers, int64_t nrows, int64_t *out, int memspace, uint32_t flags) {
+    (void)flags;
+    if (!ctx || slot < 0 || slot >= ctx->nslots || nkeys < 1 || nkeys > B200_MAX_COMBINE || !sets || !keys || !multipliers || nrows < 0 || (nrows && !out)) {
+        set_error("b200_set_combine: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    if (!nrows)
+        return B200_OK;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    CombineParams p;
+    memset(&p, 0, sizeof p);
+    p.nkeys = nkeys;
+    for (int k = 0; k < nkeys; k++) {
+        b200_set *s = sets[k];
+        if (!s || s->ctx != ctx || !keys[k]) {
+            set_error("b200_set_combine: key %d: set / column missing or from another context", k);
+            return B200_ERR_INVALID;
+        }
+        std::lock_guard<std::mutex> g(s->mu);
+        B200_CHECK(set_finalize(s));
+        p.probe[k] = s->probe;
+        p.mask[k] = s->probe_cap - 1;
+        p.sentinel[k] = s->sentinel_ordinal;
+        p.nan_ord[k] = s->nan_count > 0 ? s->nan_value : -1;
+        p.null_ord[k] = s->null_count > 0 ? s->null_value : -1;
+        p.mult[k] = multipliers[k];
+        p.dtype[k] = s->dtype;
+        p.isz[k] = (int)dtype_size(s->dtype);
+    }
+    Slot *sl = ctx->slots[slot];
+    std::lock_guard<std::mutex> gs(sl->mu);
+    Stager stg{ctx, sl, memspace};
+    for (int k = 0; k < nkeys; k++) {
+        stg.plan(keys[k], (size_t)nrows * p.isz[k]);
+        if (masks && masks[k])
+            stg.plan(masks[k], (size_t)nrows);
+    }
+    B200_CHECK(stg.commit());
+    for (int k = 0; k < nkeys; k++) {
+        p.keys[k] = stg.dev(keys[k]);
+        p.masks[k] = masks && masks[k] ? static_cast<const uint8_t *>(stg.dev(masks[k])) : nullptr;
+    }
+    long long *d_out = reinterpret_cast<long long *>(out);
+    const bool out_host = memspace == B200_MEM_HOST || (memspace == B200_MEM_MIXED && !is_device_pointer(out));
+    if (out_host)
+        B200_CUDA(cudaMalloc(&d_out, nrows * 8));
+    k_set_combine<<<nblocks((unsigned long long)nrows), 256, 0, sl->stream>>>(p, nrows, d_out);
+    B200_CUDA(cudaGetLastError());
+    if (out_host) {
+        B200_CUDA(cudaMemcpyAsync(out, d_out, nrows * 8, cudaMemcpyDeviceToHost, sl->stream));
+        B200_CUDA(cudaStreamSynchronize(sl->stream));
+        cudaFree(d_out);
+    } else if (memspace != B200_MEM_DEVICE) {
+        B200_CUDA(cudaStreamSynchronize(sl->stream)); // the caller's host key buffers are only valid during the call
+    }
+    return B200_OK;
 }
 
 // hash_base::bytes_used (src/hash_primitives.hpp:62-69): sum over maps of size * (sizeof(key) + sizeof(value))

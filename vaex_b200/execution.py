@@ -64,7 +64,7 @@ class Executor:
         if row_count is None:
             row_count = len(columns[needed[0]]) if needed else 0
         self.passes += 1
-        device = needed and all(_is_device(columns[e]) for e in needed)
+        device = needed and all(_is_device(columns[e]) or (getattr(columns[e], "device_virtual", False) and all(_is_device(c) for c in columns[e].columns)) for e in needed)
         errors = []
 
         def feed(thread_index, i1, i2):
@@ -72,7 +72,8 @@ class Executor:
                 if t.stopped or t.part.stopped:
                     t.stopped = True
                     continue
-                blocks = [columns[e][i1:i2] for e in t.expressions]
+                # virtual columns evaluated on the device (hash.CombinedCodes) are produced on this worker's slot
+                blocks = [columns[e].chunk(thread_index, i1, i2) if getattr(columns[e], "device_virtual", False) else columns[e][i1:i2] for e in t.expressions]
                 sel = [None if s is None else s[i1:i2] for s in t.selections]
                 try:
                     t.part.process(thread_index, i0 + i1, i0 + i2, None, sel, blocks)

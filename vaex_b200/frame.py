@@ -19,6 +19,8 @@ def _is_device(x):
 
 
 def _dtype_of(ar):
+    if getattr(ar, "device_virtual", False):  # device-evaluated virtual column (hash.CombinedCodes)
+        return ar.dtype
     if _is_device(ar):
         return np.dtype(ar.__cuda_array_interface__["typestr"])
     return np.asarray(ar).dtype if not np.ma.isMaskedArray(ar) else ar.dtype
@@ -190,8 +192,8 @@ class Frame:
         return keys
 
     # ---- groupby ------------------------------------------------------------------------------------------------------
-    def groupby(self, by, agg=None, sort=False, fused=True):
-        gb = GroupBy(self, by, sort=sort, fused=fused)
+    def groupby(self, by, agg=None, sort=False, fused=True, combine=False):
+        gb = GroupBy(self, by, sort=sort, fused=fused, combine=combine)
         return gb.agg(agg) if agg is not None else gb
 
 
@@ -203,10 +205,16 @@ class GroupBy:
     reference writes and re-reads (vaex/functions.py:2454-2463 + BinnerOrdinal) never exists; ``fused=False`` reproduces
     the reference's map_ordinal -> BinnerOrdinal data flow.  Keys come out in ordinal (first-seen) order, or sorted."""
 
-    def __init__(self, df, by, sort=False, fused=True):
+    def __init__(self, df, by, sort=False, fused=True, combine=False):
+        """combine: False (dense cartesian grid over the keys' ordinals), True, or 'auto' = combine when the dense grid would hold
+        fewer than 10 rows per cell (vaex/groupby.py:653-668): the keys' ordinals are fused into one int64 code on the device
+        (hash.CombinedCodes) and the groupby runs over the distinct codes — the reference's sparse `_combine` path
+        (vaex/groupby.py:526-584)."""
         self.df = df
         self.by = [by] if isinstance(by, str) else list(by)
         self.fused = fused
+        self.sort = sort
+        self.combined = None
         self.hash_maps = []
         for name in self.by:
             col = df.columns[name]
@@ -219,6 +227,35 @@ class GroupBy:
             if sort:
                 hm = hm.sorted()
             self.hash_maps.append(hm)
+        cells = 1
+        for hm in self.hash_maps:
+            cells *= len(hm)
+        if len(self.by) >= 2 and cells > 0 and (combine is True or (combine == "auto" and df.length / cells < 10)):
+            self._combine()
+
+    _COMBINED = "__combined_codes"
+
+    def _combine(self):
+        # cumulative_counts of vaex/groupby.py:548-556: decreasing products, the last multiplier is 1
+        counts = [len(hm) for hm in self.hash_maps]
+        total = 1
+        for c in counts:
+            total *= c
+        if total >= 2 ** 63 - 1:
+            raise NotImplementedError("the cartesian product of the key counts overflows 64 bits (the reference combines recursively here)")
+        multipliers = [1] * len(counts)
+        for i in range(len(counts) - 2, -1, -1):
+            multipliers[i] = multipliers[i + 1] * counts[i + 1]
+        df = self.df
+        codes = _hash.CombinedCodes([df.columns[name] for name in self.by], self.hash_maps, multipliers)
+        part = taskpart.TaskPartHashmapUniqueCreate(None, self._COMBINED, np.dtype("int64"), nthreads=1)
+        task = execution.Task(part)
+        ex = execution.Executor(1, chunk_size_max=df.executor.chunk_size_max)
+        ex.execute({self._COMBINED: codes}, [task], df.length)
+        hm = task.result
+        if self.sort:
+            hm = hm.sorted()  # parents are sorted, so code order == lexicographic key order
+        self.combined = (codes, hm)
 
     def keys(self):
         return [hm.keys() for hm in self.hash_maps]
@@ -240,6 +277,22 @@ class GroupBy:
         labels.append("__count")
         columns = dict(df.columns)
         specs = []
+        if self.combined is not None:
+            codes, chm = self.combined
+            columns[self._COMBINED] = codes
+            frame = Frame(columns, executor=df.executor)
+            spec = {"binner-type": "hash", "expression": self._COMBINED, "dtype": "<i8", "hash_map_unique": chm}
+            grids = frame._agg(descs, binby=[spec], edges=True)
+            counts = grids[-1][:-2]
+            keep = counts > 0
+            group_codes = np.asarray(chm.keys())[keep]
+            out = {}
+            for name, hm, ordinals in zip(self.by, self.hash_maps, codes.decode(group_codes)):
+                out[name] = hm.keys()[ordinals]
+            for label, g in zip(labels[:-1], grids[:-1]):
+                out[label] = g[:-2][keep]
+            out["count"] = counts[keep]
+            return out
         for name, hm in zip(self.by, self.hash_maps):
             dtype = _dtype_of(df.columns[name])
             if self.fused:

@@ -150,3 +150,86 @@ class HashMapUnique:
 
     def __sizeof__(self):
         return self._internal.__sizeof__()
+
+
+class CombinedCodes:
+    """The combined group code of a sparse multi-key groupby as a virtual int64 column that is evaluated ON THE DEVICE, chunk
+    by chunk, inside the executor's feed loop — the reference builds it as the expression
+    ``sum_k _ordinal_values(key_k, hash_map_k).astype(...) * cumulative_counts[k+1]`` (vaex/groupby.py:555-566,
+    vaex/functions.py:2454-2463) and evaluates it with numpy per chunk.
+
+    ``chunk(thread_index, i1, i2)`` runs one fused lookup kernel (``b200_set_combine``) on the slot of that executor thread
+    and returns a device array; the task part that consumes it runs on the same slot, i.e. the same CUDA stream."""
+
+    device_virtual = True  # the executor calls chunk(thread_index, i1, i2) instead of slicing
+
+    def __init__(self, columns, hash_maps, multipliers):
+        if not 1 <= len(columns) <= 8:
+            raise ValueError("between 1 and 8 key columns can be combined")
+        assert len(columns) == len(hash_maps) == len(multipliers)
+        self.columns = list(columns)
+        self.hash_maps = list(hash_maps)
+        self.multipliers = [int(m) for m in multipliers]
+        self.dtype = np.dtype("int64")
+        self._ctx_cached = None
+        self._buffers = {}
+
+    def __len__(self):
+        return len(self.columns[0])
+
+    @property
+    def _ctx(self):
+        if self._ctx_cached is None:
+            from . import _lib
+            self._ctx_cached = _lib.context()
+        return self._ctx_cached
+
+    def _buffer(self, thread_index, n):
+        import torch
+        buf = self._buffers.get(thread_index)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n, 1), dtype=torch.int64, device=f"cuda:{self._ctx.device}")
+            self._buffers[thread_index] = buf
+        return buf[:n]
+
+    def chunk(self, thread_index, i1, i2):
+        import ctypes as C
+        from . import _lib
+        n = i2 - i1
+        out = self._buffer(thread_index, n)
+        if n == 0:
+            return out
+        nk = len(self.columns)
+        keep, kptr, mptr, spaces = [], (C.c_void_p * nk)(), (C.c_void_p * nk)(), set()
+        for k, col in enumerate(self.columns):
+            part = col[i1:i2]
+            mask = None
+            if isinstance(part, np.ndarray) and np.ma.isMaskedArray(part):
+                mask = np.ma.getmaskarray(part)
+                part = part.data
+            if isinstance(part, np.ndarray) and not part.dtype.isnative:
+                part = part.astype(part.dtype.newbyteorder("="))
+            c = _lib.column(part)
+            if c.dtype.itemsize != self.hash_maps[k].dtype.itemsize:
+                raise RuntimeError("stride not equal to bytesize for key values")
+            keep.append(c)
+            spaces.add(c.memspace)
+            kptr[k] = c.ptr
+            if mask is not None:
+                m = _lib.mask_column(mask)
+                keep.append(m)
+                mptr[k] = m.ptr
+        sets = (C.c_void_p * nk)(*[hm._internal._h for hm in self.hash_maps])
+        mult = (C.c_int64 * nk)(*self.multipliers)
+        memspace = _lib.MEM_DEVICE if spaces == {_lib.MEM_DEVICE} else _lib.MEM_MIXED
+        _lib.check(_lib.lib().b200_set_combine(self._ctx._h, self._ctx.slot(thread_index), nk, sets, kptr, mptr, mult, n, out.data_ptr(), memspace, 0))
+        return out
+
+    def decode(self, codes):
+        """group code -> ordinal of every parent key (the div/mod chain of GrouperCombined, vaex/groupby.py:352-358)"""
+        codes = np.asarray(codes, dtype=np.int64)
+        out, left = [], codes
+        for m in self.multipliers:
+            out.append(left // m)
+            left = left % m
+        return out

@@ -204,9 +204,9 @@ class Grid:
         for k, agg in enumerate(aggregators):
             keep += agg._fill(A[k], thread)
         spaces = {c.memspace for c in keep}
-        if len(spaces) > 1:
-            raise RuntimeError("host and device columns cannot be mixed in one bin() call")
-        memspace = spaces.pop() if spaces else _lib.MEM_HOST
+        # host and device columns in one call (device-computed group codes next to host value columns): every pointer is
+        # classified by the library
+        memspace = _lib.MEM_MIXED if len(spaces) > 1 else (spaces.pop() if spaces else _lib.MEM_HOST)
         for c in keep:
             if c.length < length:
                 raise RuntimeError(f"a column of length {c.length} is shorter than the {length} rows to bin")

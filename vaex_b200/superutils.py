@@ -84,14 +84,13 @@ class _OrderedSet:
             mcol = _lib.mask_column(masks)
             if mcol.length != col.length:
                 raise RuntimeError("array and mask should be of same size")
-            if mcol.memspace != col.memspace:
-                raise RuntimeError("host and device columns cannot be mixed")
         n = col.length
         rv = bool(opts["return_values"])
         out_values = np.empty(n if rv else 1, np.int64)
         out_map = np.empty(n if rv else 1, np.int16)
         _lib.check(_lib.lib().b200_set_update(self._h, 0, col.ptr, None if mcol is None else mcol.ptr, n, int(opts["start_index"]), int(rv),
-                                              out_values.ctypes.data, out_map.ctypes.data, col.memspace, 0))
+                                              out_values.ctypes.data, out_map.ctypes.data,
+                                              col.memspace if mcol is None or mcol.memspace == col.memspace else _lib.MEM_MIXED, 0))
         if rv:
             return out_values, out_map
         return None
