@@ -72,7 +72,10 @@ typedef enum {
 
 typedef enum {
     B200_AGG_COUNT = 0, B200_AGG_SUM, B200_AGG_SUM_MOMENT, B200_AGG_MIN, B200_AGG_MAX,
-    B200_AGG_FIRST, B200_AGG_LAST
+    B200_AGG_FIRST, B200_AGG_LAST,
+    B200_AGG_NUNIQUE /* AggNUnique_<T>(grid, grids, threads, dropmissing, dropnan) (src/agg_nunique.cpp): `moment` bit 0 = dropmissing,
+                        bit 1 = dropnan.  b200_agg_input: `mask` = validity (1 = value present, 0 = null row: the reference's
+                        data mask), `order` = selection mask (uint8, 1 = the row takes part: set_selection_mask); both nullable */
 } b200_agg_op;
 
 /* where the column pointers of a call live.  MIXED: every pointer is classified on its own (cudaPointerGetAttributes);

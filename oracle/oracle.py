@@ -79,6 +79,10 @@ def lib():
         L.orc_set_isin.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_set_merge.restype = C.c_int
         L.orc_set_merge.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_scalar_to_bins.restype = C.c_int
+        L.orc_scalar_to_bins.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.orc_ordinal_to_bins.restype = C.c_int
+        L.orc_ordinal_to_bins.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -95,9 +99,10 @@ def ordinal(data, count, min_value=0, allow_other=False, invert=False, mask=None
     return dict(kind="ordinal", data=data, mask=mask, count=int(count), min_value=int(min_value), allow_other=bool(allow_other), invert=bool(invert))
 
 
-def agg(op, data=None, mask=None, moment=None, order=None):
-    """Aggregator spec; ``mask`` follows the aggregator convention (1 = use the row)."""
-    return dict(op=op, data=data, mask=mask, moment=moment, order=order)
+def agg(op, data=None, mask=None, moment=None, order=None, selection=None, dropmissing=False, dropnan=False):
+    """Aggregator spec; ``mask`` follows the aggregator convention (1 = use the row).  ``nunique`` only: ``mask`` = 0 marks a null
+    row, ``selection`` = 0 a row that is skipped (set_selection_mask), plus the dropmissing / dropnan constructor flags."""
+    return dict(op=op, data=data, mask=mask, moment=moment, order=order, selection=selection, dropmissing=bool(dropmissing), dropnan=bool(dropnan))
 
 
 def binner_shape(b):
@@ -155,6 +160,13 @@ def binby(binners, aggs, length=None):
     cells = int(np.prod(shapes)) if shapes else 1
     if length is None:
         length = 0
+    # nunique is restated in Python (nunique() below); everything else goes through the C driver
+    nunique_at = {k: a for k, a in enumerate(aggs) if a["op"] == "nunique"}
+    if nunique_at:
+        rest = [a for a in aggs if a["op"] != "nunique"]
+        others = iter(binby(binners, rest, length) if rest else [])
+        return [nunique(binners, a["data"], a["mask"], a.get("selection"), a.get("dropmissing", False), a.get("dropnan", False), length)
+                if k in nunique_at else next(others) for k, a in enumerate(aggs)]
     na = len(aggs)
     A = (_Agg * max(na, 1))()
     outs = []
@@ -211,6 +223,68 @@ def binby(binners, aggs, length=None):
         else:
             results.append(o.reshape(shapes, order="F"))
     return results
+
+
+def flat_indices(binners, length=None):
+    """The index half of Grid::bin_ (agg.hpp:106-124): every binner's to_bins accumulated into one flat cell index per row."""
+    L = lib()
+    out, stride, shapes = None, 1, []
+    for b in binners:
+        data = np.ascontiguousarray(b["data"])
+        if length is None:
+            length = len(data)
+        if out is None:
+            out = np.zeros(length, np.uint64)
+        mask = _mask_u8(b["mask"])
+        if b["kind"] == "scalar":
+            rc = L.orc_scalar_to_bins(dtype_code(data.dtype), int(is_swapped(data)), _ptr(data), _ptr(mask), b["vmin"], b["vmax"], b["bins"], 0, length, stride,
+                                      out.ctypes.data)
+        else:
+            rc = L.orc_ordinal_to_bins(dtype_code(data.dtype), int(is_swapped(data)), _ptr(data), _ptr(mask), b["count"], b["min_value"], int(b["allow_other"]),
+                                       int(b["invert"]), 0, length, stride, out.ctypes.data)
+        if rc:
+            raise RuntimeError(f"oracle error {rc}")
+        shapes.append(binner_shape(b))
+        stride *= shapes[-1]
+    if out is None:
+        out = np.zeros(length or 0, np.uint64)
+    return out, shapes
+
+
+def nunique(binners, data, valid=None, selection=None, dropmissing=False, dropnan=False, length=None):
+    """AggNUniquePrimitive (src/agg_nunique.cpp): aggregate (:57-86) keeps one counter<T> per cell — a row outside
+    ``selection`` (1 = take part) is skipped, a row with ``valid`` == 0 is a null, NaN a nan, the rest distinct keys; get_result
+    (:16-42) returns keys + (any null) + (any nan), and dropmissing / dropnan subtract the cell's null / nan ROW counts
+    (``null_count`` / ``nan_count`` are incremented per row, src/hash_primitives.hpp:296-301).  Restated with Python sets."""
+    data = np.asarray(data)
+    if length is None:
+        length = len(data)
+    idx, shapes = flat_indices(binners, length)
+    cells = int(np.prod(shapes)) if shapes else 1
+    native = data.astype(data.dtype.newbyteorder("=")) if is_swapped(data) else data
+    keys = [set() for _ in range(cells)]
+    nan_rows = np.zeros(cells, np.int64)
+    null_rows = np.zeros(cells, np.int64)
+    isnan = np.isnan(native) if native.dtype.kind == "f" else np.zeros(length, bool)
+    # keys are told apart by their BITS: the hash of a double is the hash of its bit pattern (src/hash.hpp:50-152), so -0.0 and
+    # 0.0 live in different buckets and are never compared — two keys (pinned by the golden vectors)
+    bits = np.ascontiguousarray(native).view("u%d" % native.dtype.itemsize).tolist()
+    for j in range(length):
+        if selection is not None and not selection[j]:
+            continue
+        c = int(idx[j])
+        if valid is not None and not valid[j]:
+            null_rows[c] += 1
+        elif isnan[j]:
+            nan_rows[c] += 1
+        else:
+            keys[c].add(bits[j])
+    out = np.array([len(k) for k in keys], np.int64) + (null_rows > 0) + (nan_rows > 0)
+    if dropmissing:
+        out -= null_rows
+    if dropnan:
+        out -= nan_rows
+    return out.reshape(shapes, order="F") if shapes else out.reshape(())
 
 
 def hash64(x):

@@ -110,6 +110,8 @@ class RefBinby:
                 if sfx.endswith("_non_native"):
                     name += "_non_native"
                 agg = getattr(superagg, name)(self.grid, grids, nthreads, op == "last")
+            elif op == "nunique":  # vaex/agg.py:356-369: grids = 1, one shared thread-safe set structure
+                agg = getattr(superagg, "AggNUnique_" + sfx)(self.grid, 1, nthreads, a.get("dropmissing", False), a.get("dropnan", False))
             else:
                 raise ValueError(op)
             self.aggs.append(agg)
@@ -142,6 +144,13 @@ class RefBinby:
                 keep.append(m)
             else:
                 agg.clear_data_mask(thread)
+            if spec["op"] == "nunique":
+                if spec.get("selection") is not None:
+                    m = np.ascontiguousarray(spec["selection"][i1:i2])
+                    agg.set_selection_mask(thread, m)
+                    keep.append(m)
+                else:
+                    agg.clear_selection_mask(thread)
         self.grid.bin(thread, self.aggs, i2 - i1)
 
     def run(self, length, chunk=None):

@@ -49,6 +49,10 @@ def cases():
                 c[f"a{k}_moment"] = a["moment"]
             if a.get("order") is not None:
                 c[f"a{k}_order"] = a["order"]
+            if a.get("selection") is not None:
+                c[f"a{k}_selection"] = a["selection"]
+            if a["op"] == "nunique":
+                c[f"a{k}_drop"] = np.array([a["dropmissing"], a["dropnan"]])
             if np.ma.isMaskedArray(r):
                 c[f"a{k}_result"] = np.asarray(r.data)
                 c[f"a{k}_result_mask"] = np.ma.getmaskarray(r)
@@ -99,6 +103,31 @@ def cases():
     fv = rng.normal(0, 1, n)
     fo = rng.integers(0, 40, n).astype("i8")
     add("first_last", [O.scalar(fx, 0, 4, 4)], [O.agg("first", fv, None, order=fo), O.agg("last", fv, None, order=fo), O.agg("first", fv, None)], n)
+    # AggNUnique (src/agg_nunique.cpp; tests/agg_test.py:294-333): the float KAT of the reference test, then random cells with
+    # several NaN / null rows each (dropmissing / dropnan subtract ROW counts), selections, every dtype family, byte-swapped input
+    kx = np.array([0, 0, 0, 0, 0, 1, 1, 1, 2], dtype="f8")
+    ks = np.array([1.2, 1.2, 2.5, 3.7, np.nan, 3.7, 4.8, 3.7, 1.2])
+    add("nunique_kat", [O.scalar(kx, 0, 3, 3)], [O.agg("nunique", ks), O.agg("nunique", ks, dropnan=True)], 9)
+    ky = np.array([1, 1, 0, 1, 0, 0, 0, 1, 1], dtype="u1")
+    add("nunique_kat_filtered", [O.scalar(kx, 0, 3, 3)], [O.agg("nunique", ks, selection=(ky == 0).astype("u1"))], 9)
+    n = 3000
+    gx = rng.uniform(0, 5, n)
+    gy = rng.integers(0, 4, n).astype("i4")
+    for dt in ("f8", "f4", "i8", "i2", "u1", "?", ">f8", ">i4"):
+        d = np.dtype(dt)
+        if d.kind == "f":
+            v = (rng.integers(-6, 6, n) * 0.5).astype(d)
+            v[rng.random(n) < 0.1] = np.nan
+            v[rng.random(n) < 0.05] = -0.0
+        elif d.kind == "b":
+            v = rng.integers(0, 2, n).astype(d)
+        else:
+            v = rng.integers(0 if d.kind == "u" else -8, 9, n).astype(d)
+        valid = (rng.random(n) < 0.85).astype("u1")
+        sel = (rng.random(n) < 0.7).astype("u1")
+        add("nunique_" + d.name + ("_be" if dt.startswith(">") else ""), [O.scalar(gx, 0, 5, 6), O.ordinal(gy, 4)],
+            [O.agg("nunique", v), O.agg("nunique", v, valid, dropmissing=True), O.agg("nunique", v, valid, selection=sel, dropnan=True),
+             O.agg("nunique", v, valid, selection=sel, dropmissing=True, dropnan=True), O.agg("count", v)], n)
     return out
 
 

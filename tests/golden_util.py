@@ -32,7 +32,9 @@ def binby_case(c):
         if data is not None:
             data = data.view(np.dtype(str(c[f"a{k}_dtype"])))
         moment = int(c[f"a{k}_moment"]) if f"a{k}_moment" in c else None
-        aggs.append(O.agg(str(c[f"a{k}_op"]), data, c.get(f"a{k}_mask"), moment=moment, order=c.get(f"a{k}_order")))
+        drop = c.get(f"a{k}_drop", [False, False])
+        aggs.append(O.agg(str(c[f"a{k}_op"]), data, c.get(f"a{k}_mask"), moment=moment, order=c.get(f"a{k}_order"), selection=c.get(f"a{k}_selection"),
+                          dropmissing=bool(drop[0]), dropnan=bool(drop[1])))
         r = c[f"a{k}_result"]
         if f"a{k}_result_mask" in c:
             r = np.ma.array(r, mask=c[f"a{k}_result_mask"])

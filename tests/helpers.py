@@ -59,6 +59,8 @@ class B200Binby:
                 sfx2 = "int64" if order is None else np.asarray(order).dtype.newbyteorder("=").name
                 name = "AggFirst_" + np.asarray(data).dtype.newbyteorder("=").name + "_" + sfx2 + ("_non_native" if sfx.endswith("_non_native") else "")
                 agg = getattr(superagg, name)(self.grid, 1, nthreads, op == "last")
+            elif op == "nunique":
+                agg = getattr(superagg, "AggNUnique_" + sfx)(self.grid, 1, nthreads, a.get("dropmissing", False), a.get("dropnan", False))
             else:
                 raise ValueError(op)
             self.aggs.append(agg)
@@ -81,6 +83,11 @@ class B200Binby:
                 agg.set_data_mask(thread, conv(np.asarray(spec["mask"])[sl]))
             else:
                 agg.clear_data_mask(thread)
+            if spec["op"] == "nunique":
+                if spec.get("selection") is not None:
+                    agg.set_selection_mask(thread, conv(np.asarray(spec["selection"])[sl]))
+                else:
+                    agg.clear_selection_mask(thread)
         self.grid.bin(thread, self.aggs, i2 - i1, row_offset=i1)
 
     def run(self, length, chunk=None, device=False):

@@ -267,3 +267,52 @@ def test_groupby_sparse_combined_matches_numpy(device, sort, oracle):
         assert np.array_equal(np.asarray(out["k1"]), sets[0].key_array()[o1])
         assert np.array_equal(np.asarray(out["k2"], dtype="f8"), sets[1].key_array()[o2], equal_nan=True)
         assert np.array_equal(np.asarray(out["k3"]), sets[2].key_array()[o3])
+
+
+def test_nunique_reference_kats():
+    # tests/agg_test.py:294-333 (float variant: the strings mapped to floats, None -> NaN), :583-586 (no binby)
+    from vaex_b200.execution import Executor
+    from vaex_b200.frame import Frame
+    x = np.array([0, 0, 0, 0, 0, 1, 1, 1, 2], dtype="i8")
+    s = np.array([1.2, 1.2, 2.5, 3.7, np.nan, 3.7, 4.8, 3.7, 1.2])
+    y = np.array([1, 1, 0, 1, 0, 0, 0, 1, 1])
+    for chunk in (None, 2):
+        df = Frame(dict(x=x, s=s), executor=Executor(nthreads=2, chunk_size=chunk))
+        df.categorize("x", min_value=0, count=3)
+        assert df.nunique("s", binby="x").tolist() == [4, 2, 1]
+        assert df.nunique("s", binby="x", dropnan=True).tolist() == [3, 2, 1]
+        assert df.nunique("s", binby="x", selection=(y == 0)).tolist() == [2, 2, 0]
+    df = Frame(dict(x=np.array([1, 2, 3], dtype="i8")))
+    r = df.nunique("x")
+    assert r.ndim == 0 and r.item() == 3
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_nunique_large_matches_numpy(device):
+    """2M rows, ~600k distinct (cell, value) pairs: table growth + rehash across chunks, several executor threads sharing the one
+    aggregator (vaex/agg.py:357: 'using a shared hashmap, which is thread safe'), masked values, NaN; against numpy."""
+    import torch
+    from vaex_b200.execution import Executor
+    from vaex_b200.frame import Frame
+    rng = np.random.default_rng(33)
+    n = 2_000_000
+    g = rng.integers(0, 50, n).astype("i4")
+    v = rng.integers(0, 20_000, n).astype("f8")
+    v[rng.random(n) < 0.001] = np.nan
+    vm = np.ma.array(v, mask=rng.random(n) < 0.002)
+    cols = dict(g=g, v=v) if device else dict(g=g, v=vm)
+    if device:
+        cols = {k: torch.from_numpy(a).cuda() for k, a in cols.items()}
+    df = Frame(cols, executor=Executor(nthreads=3, chunk_size=300_000))
+    df.categorize("g", min_value=0, count=50)
+    got = df.nunique("v", binby="g")
+    got_drop = df.nunique("v", binby="g", dropna=True)
+    valid = np.ones(n, bool) if device else ~vm.mask
+    for c in range(50):
+        inc = g == c
+        vals = v[inc & valid]
+        nn = vals[~np.isnan(vals)]
+        distinct = len(np.unique(nn))
+        n_nan, n_null = int(np.isnan(vals).sum()), int((inc & ~valid).sum())
+        assert got[c] == distinct + (n_nan > 0) + (n_null > 0)
+        assert got_drop[c] == distinct + (n_nan > 0) + (n_null > 0) - n_nan - n_null  # row counts, like the reference

@@ -32,8 +32,12 @@ def test_descriptor_specs_match_vaex_encoding():
     # mean / std decompose into the same primitives as vaex/agg.py:386-455
     assert [p.short_name for p in agg.mean("x").primitives()] == ["sum", "count"]
     assert [p.short_name for p in agg.std("x").primitives()] == ["_sum_moment", "sum", "count"]
+    # vaex/agg.py:344-350, 600-612: dropna sets both flags; flags are only encoded when set
+    assert agg.nunique("x").encode() == {"aggregation": "nunique", "expressions": ["x"]}
+    spec = {"aggregation": "nunique", "expressions": ["x"], "dropmissing": True, "dropnan": True}
+    assert agg.nunique("x", dropna=True).encode() == spec and agg.from_spec(spec).encode() == spec
     with pytest.raises(ValueError):
-        agg.from_spec({"aggregation": "nunique", "expressions": ["x"]})
+        agg.from_spec({"aggregation": "list", "expressions": ["x"]})
 
 
 def test_prepare_types_and_class_lookup():

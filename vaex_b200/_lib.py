@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200agg.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "binby.cu", "fast.cu", "first.cu", "hashset.cu", "tilecount.cu", "tilesort.cu"]
+SOURCES = ["api.cu", "binby.cu", "fast.cu", "first.cu", "hashset.cu", "nunique.cu", "tilecount.cu", "tilesort.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
@@ -23,7 +23,7 @@ DTYPES = ["float64", "float32", "int64", "int32", "int16", "int8", "uint64", "ui
 DTYPE_CODE = {n: i for i, n in enumerate(DTYPES)}
 F64, F32, I64, I32, I16, I8, U64, U32, U16, U8, BOOL = range(11)
 BINNER_SCALAR, BINNER_ORDINAL, BINNER_HASH = 0, 1, 2
-AGG_COUNT, AGG_SUM, AGG_SUM_MOMENT, AGG_MIN, AGG_MAX, AGG_FIRST, AGG_LAST = range(7)
+AGG_COUNT, AGG_SUM, AGG_SUM_MOMENT, AGG_MIN, AGG_MAX, AGG_FIRST, AGG_LAST, AGG_NUNIQUE = range(8)
 MEM_HOST, MEM_DEVICE, MEM_MIXED = 0, 1, 2
 FLAG_ASYNC_HOST = 1
 ERR_NODATA = -3

@@ -4,7 +4,8 @@ Reference: packages/vaex-core/vaex/agg.py:221-335 (AggregatorDescriptorBasic: en
 grid-count heuristic and memory accounting, get_result edge slicing), :386-523 (mean / var / std / skew / kurtosis as
 combinations of primitive grids + ``finish``), :525-606 (count, sum, mean, min, max, first, last, std, var, ...).
 The primitive aggregations run on the GPU (vaex_b200.superagg); ``finish`` is O(cells) numpy like in the reference.
-Out of scope here: nunique, list, describe, string/object columns.
+nunique (vaex/agg.py:338-369, 600-612) runs on the device too.  Out of scope here: list, describe, string/object
+columns.
 """
 import operator
 from functools import reduce
@@ -129,6 +130,31 @@ class AggregatorDescriptorBasic(AggregatorDescriptor):
         return grid
 
 
+class AggregatorDescriptorNUnique(AggregatorDescriptorBasic):
+    """vaex/agg.py:338-369: one shared (thread safe) set structure, grids = 1, int64 result."""
+
+    def __init__(self, name, expression, short_name, dropmissing, dropnan, selection=None, edges=False):
+        super().__init__(name, expression, short_name, selection=selection, edges=edges)
+        self.dropmissing = dropmissing
+        self.dropnan = dropnan
+
+    def encode(self, encoding=None):
+        spec = super().encode(encoding)
+        if self.dropmissing:
+            spec["dropmissing"] = self.dropmissing
+        if self.dropnan:
+            spec["dropnan"] = self.dropnan
+        return spec
+
+    def _prepare_types(self, dtypes):
+        super()._prepare_types(dtypes)
+        self.dtype_out = np.dtype("int64")
+
+    def _create_operation(self, grid, nthreads):
+        agg_op_type = find_type_from_dtype(superagg, self.name + "_", self.dtype_in)
+        return agg_op_type(grid, 1, nthreads, self.dropmissing, self.dropnan)
+
+
 class AggregatorDescriptorMulti(AggregatorDescriptor):
     """mean / var / std / skew / kurtosis: several primitive grids + finish() (vaex/agg.py:373-523)."""
 
@@ -238,7 +264,17 @@ def from_spec(spec):
     if name in ("first", "last"):
         f = first if name == "first" else last
         return f(exprs[0], exprs[1] if len(exprs) > 1 else None, **kw)
+    if name == "nunique":
+        return nunique(exprs[0], dropnan=spec.get("dropnan", False), dropmissing=spec.get("dropmissing", False), **kw)
     raise ValueError(f"aggregation {name!r} is not on the B200 hot path")
 
 
-aggregates = {f.__name__: f for f in (count, sum, min, max, first, last, mean, var, std, skew, kurtosis)}
+def nunique(expression, dropna=False, dropnan=False, dropmissing=False, selection=None, edges=False):
+    """Number of unique items per bin (vaex/agg.py:600-612)."""
+    if dropna:
+        dropnan = True
+        dropmissing = True
+    return AggregatorDescriptorNUnique("AggNUnique", [expression], "nunique", dropmissing, dropnan, selection=selection, edges=edges)
+
+
+aggregates = {f.__name__: f for f in (count, sum, min, max, first, last, mean, var, std, skew, kurtosis, nunique)}

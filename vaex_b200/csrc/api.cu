@@ -119,6 +119,14 @@ static int64_t narrow_limit(int dtype, bool mx) {
 }
 
 static int agg_fill(b200_agg *a, cudaStream_t st) {
+    if (a->op == B200_AGG_NUNIQUE) {
+        B200_CUDA(cudaMemsetAsync(a->grid, 0, (a->cells ? a->cells : 1) * 8 * 3, st));
+        if (a->ntable)
+            B200_CUDA(cudaMemsetAsync(a->ntable, 0xff, a->ncap * 16, st));
+        B200_CUDA(cudaMemsetAsync(a->ntotal, 0, 8, st));
+        a->npairs = 0;
+        return B200_OK;
+    }
     if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST) {
         // src/agg_first.cpp:19-26: value 99, order limits, cell_masked 1; the packed {key,row} state starts at the maximum
         const int isz = dtype_size(a->dtype), isz2 = dtype_size(a->dtype2);
@@ -291,7 +299,7 @@ int b200_ctx_stream(b200_ctx *ctx, int slot, void **stream_out) {
 
 // ---- aggregators -----------------------------------------------------------------------------------
 int b200_agg_create(b200_ctx *ctx, int op, int dtype, int dtype2, int byteswap, uint32_t moment, uint64_t cells, b200_agg **out) {
-    if (!ctx || !out || op < B200_AGG_COUNT || op > B200_AGG_LAST || dtype < 0 || dtype >= B200_NDTYPE || dtype2 < 0 || dtype2 >= B200_NDTYPE) {
+    if (!ctx || !out || op < B200_AGG_COUNT || op > B200_AGG_NUNIQUE || dtype < 0 || dtype >= B200_NDTYPE || dtype2 < 0 || dtype2 >= B200_NDTYPE) {
         set_error("b200_agg_create: invalid argument");
         return B200_ERR_INVALID;
     }
@@ -305,7 +313,8 @@ int b200_agg_create(b200_ctx *ctx, int op, int dtype, int dtype2, int byteswap, 
     a->moment = moment;
     a->cells = cells;
     switch (op) {
-    case B200_AGG_COUNT: a->cell_dtype = B200_I64; break;
+    case B200_AGG_COUNT:
+    case B200_AGG_NUNIQUE: a->cell_dtype = B200_I64; break;
     case B200_AGG_SUM:
     case B200_AGG_SUM_MOMENT: a->cell_dtype = dtype_upcast(dtype); break;
     case B200_AGG_MIN:
@@ -313,7 +322,9 @@ int b200_agg_create(b200_ctx *ctx, int op, int dtype, int dtype2, int byteswap, 
     default: a->cell_dtype = dtype; break;
     }
     const size_t n = cells ? cells : 1;
-    cudaError_t e = cudaMalloc(&a->grid, n * dtype_size(a->cell_dtype));
+    cudaError_t e = cudaMalloc(&a->grid, n * dtype_size(a->cell_dtype) * (op == B200_AGG_NUNIQUE ? 3 : 1));
+    if (e == cudaSuccess && op == B200_AGG_NUNIQUE)
+        e = cudaMalloc((void **)&a->ntotal, 8);
     if (e == cudaSuccess && (op == B200_AGG_FIRST || op == B200_AGG_LAST)) {
         e = cudaMalloc(&a->state, n * 16);
         if (e == cudaSuccess)
@@ -352,6 +363,8 @@ int b200_agg_destroy(b200_agg *a) {
     cudaFree(a->state);
     cudaFree(a->order);
     cudaFree(a->cell_masked);
+    cudaFree(a->ntable);
+    cudaFree(a->ntotal);
     if (a->chain)
         cudaEventDestroy(a->chain);
     delete a;
@@ -376,7 +389,7 @@ int b200_agg_reset_on(b200_agg *a, int slot) {
         set_error("b200_agg_reset_on: invalid argument");
         return B200_ERR_INVALID;
     }
-    if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST)
+    if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST || a->op == B200_AGG_NUNIQUE)
         return b200_agg_reset(a);
     B200_CUDA(cudaSetDevice(a->ctx->device));
     return agg_fill(a, a->ctx->slots[slot]->stream);
@@ -387,8 +400,8 @@ int b200_agg_read_on(b200_agg *a, int slot, void *values_out) {
         set_error("b200_agg_read_on: invalid argument");
         return B200_ERR_INVALID;
     }
-    if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST) {
-        set_error("b200_agg_read_on: not available for first/last");
+    if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST || a->op == B200_AGG_NUNIQUE) {
+        set_error("b200_agg_read_on: not available for first/last/nunique");
         return B200_ERR_UNSUPPORTED;
     }
     B200_CUDA(cudaSetDevice(a->ctx->device));
@@ -400,7 +413,8 @@ uint64_t b200_agg_cells(const b200_agg *a) { return a ? a->cells : 0; }
 
 int b200_agg_result_dtype(const b200_agg *a) {
     switch (a->op) {
-    case B200_AGG_COUNT: return B200_I64;
+    case B200_AGG_COUNT:
+    case B200_AGG_NUNIQUE: return B200_I64;
     case B200_AGG_SUM:
     case B200_AGG_SUM_MOMENT: return dtype_upcast(a->dtype);
     default: return a->dtype;
@@ -438,6 +452,25 @@ int b200_agg_read(b200_agg *a, void *values_out, uint8_t *cell_masked_out) {
     const int rsz = dtype_size(rdt), csz = dtype_size(a->cell_dtype);
     if (!a->cells)
         return B200_OK;
+    if (a->op == B200_AGG_NUNIQUE) {
+        // src/agg_nunique.cpp:16-42: counter.count() = keys + (any null) + (any NaN); dropmissing / dropnan subtract the NUMBER OF
+        // null / NaN ROWS of the cell (null_count / nan_count are row counts there) — reproduced as is
+        std::vector<uint64_t> planes(a->cells * 3);
+        B200_CUDA(cudaMemcpy(planes.data(), a->grid, a->cells * 24, cudaMemcpyDeviceToHost));
+        int64_t *out = static_cast<int64_t *>(values_out);
+        for (uint64_t i = 0; i < a->cells; i++) {
+            const int64_t nan = (int64_t)planes[a->cells + i], null = (int64_t)planes[2 * a->cells + i];
+            int64_t c = (int64_t)planes[i] + (null > 0) + (nan > 0);
+            if (a->moment & 1)
+                c -= null;
+            if (a->moment & 2)
+                c -= nan;
+            out[i] = c;
+        }
+        if (cell_masked_out)
+            memset(cell_masked_out, 0, a->cells);
+        return B200_OK;
+    }
     if (rsz == csz) {
         B200_CUDA(cudaMemcpy(values_out, a->grid, a->cells * rsz, cudaMemcpyDeviceToHost));
     } else {
@@ -469,8 +502,8 @@ int b200_agg_write(b200_agg *a, const void *values) {
         set_error("b200_agg_write: invalid argument");
         return B200_ERR_INVALID;
     }
-    if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST) {
-        set_error("b200_agg_write: first/last grids cannot be loaded (no order state)");
+    if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST || a->op == B200_AGG_NUNIQUE) {
+        set_error("b200_agg_write: first/last/nunique grids cannot be loaded (no per-cell state)");
         return B200_ERR_UNSUPPORTED;
     }
     B200_CUDA(cudaSetDevice(a->ctx->device));
@@ -495,6 +528,10 @@ int b200_agg_merge(b200_agg *a, b200_agg *const *others, int nothers) {
     if (!a || (nothers && !others)) {
         set_error("b200_agg_merge: invalid argument");
         return B200_ERR_INVALID;
+    }
+    if (a->op == B200_AGG_NUNIQUE && nothers) {
+        set_error("merge not implemented"); // src/agg_nunique.cpp:43-46
+        return B200_ERR_UNSUPPORTED;
     }
     B200_CUDA(cudaSetDevice(a->ctx->device));
     B200_CHECK(b200_ctx_sync(a->ctx, -1));
@@ -548,6 +585,63 @@ int b200_agg_merge(b200_agg *a, b200_agg *const *others, int nothers) {
 }
 
 // ---- the hot path ----------------------------------------------------------------------------------
+// NUNIQUE: batches of rows; before every launch the pair table is made large enough for (pairs so far + rows of the batch) at
+// load <= 0.5, so an insert can never fail inside the kernel.  Callers on several slots share one table: serialised here.
+static int bin_nunique(b200_ctx *ctx, Slot *sl, b200_agg *a, const DevBinner *db, int nbinners, const void *data, const uint8_t *valid,
+                       const uint8_t *selection, int64_t nrows, bool vec) {
+    std::lock_guard<std::mutex> g(a->nmu);
+    cudaStream_t st = sl->stream;
+    NUniqueParams np;
+    memset(&np, 0, sizeof np);
+    np.nb = nbinners;
+    memcpy(np.b, db, sizeof(DevBinner) * nbinners);
+    np.dtype = a->dtype;
+    np.isz = dtype_size(a->dtype);
+    np.byteswap = a->byteswap && np.isz > 1;
+    np.data = data;
+    np.valid = valid;
+    np.selection = selection;
+    np.distinct = static_cast<unsigned long long *>(a->grid);
+    np.nan_rows = np.distinct + a->cells;
+    np.null_rows = np.distinct + 2 * a->cells;
+    np.total = a->ntotal;
+    bool v = vec && !(reinterpret_cast<uintptr_t>(data) & 15) && !(reinterpret_cast<uintptr_t>(valid) & 15) && !(reinterpret_cast<uintptr_t>(selection) & 15);
+    const int64_t batch = 1ll << 24;
+    for (int64_t r0 = 0; r0 < nrows; r0 += batch) {
+        const int64_t n = std::min<int64_t>(batch, nrows - r0);
+        uint64_t need = 1 << 12;
+        while (need < 2 * (a->npairs + (uint64_t)n))
+            need <<= 1;
+        if (need > a->ncap) {
+            unsigned long long *nt = nullptr;
+            cudaError_t e = cudaMalloc((void **)&nt, need * 16);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                set_error("nunique: out of device memory for a table of %llu slots", (unsigned long long)need);
+                return B200_ERR_NOMEM;
+            }
+            B200_CUDA(cudaMemsetAsync(nt, 0xff, need * 16, st));
+            if (a->ntable) {
+                B200_CHECK(launch_nunique_rehash(st, a->ntable, a->ncap, nt, need));
+                B200_CUDA(cudaStreamSynchronize(st));
+                cudaFree(a->ntable);
+            }
+            a->ntable = nt;
+            a->ncap = need;
+        }
+        np.table = a->ntable;
+        np.tmask = a->ncap - 1;
+        np.row0 = r0;
+        np.nrows = n;
+        B200_CHECK(launch_nunique(ctx, st, np, v));
+        unsigned long long total = 0;
+        B200_CUDA(cudaMemcpyAsync(&total, a->ntotal, 8, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        a->npairs = total;
+    }
+    return B200_OK;
+}
+
 int b200_bin(b200_ctx *ctx, int slot, const b200_binner *binners, int nbinners, const b200_agg_input *aggs, int naggs, int64_t nrows,
              int64_t row_offset, int memspace, uint32_t flags) {
     if (!ctx || slot < 0 || slot >= ctx->nslots || nbinners < 0 || nbinners > B200_MAX_BINNERS || naggs < 0 || nrows < 0 || (nbinners && !binners) ||
@@ -636,7 +730,7 @@ int b200_bin(b200_ctx *ctx, int slot, const b200_binner *binners, int nbinners, 
         if (aggs[k].data)
             stg.plan(aggs[k].data, (size_t)nrows * dtype_size(a->dtype));
         if (aggs[k].order)
-            stg.plan(aggs[k].order, (size_t)nrows * dtype_size(a->dtype2));
+            stg.plan(aggs[k].order, a->op == B200_AGG_NUNIQUE ? (size_t)nrows : (size_t)nrows * dtype_size(a->dtype2));
         if (aggs[k].mask) {
             const bool first = a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST;
             stg.plan(aggs[k].mask, first ? (size_t)std::min<int64_t>(nrows, 1024) : (size_t)nrows);
@@ -723,6 +817,11 @@ int b200_bin(b200_ctx *ctx, int slot, const b200_binner *binners, int nbinners, 
                 B200_CHECK(launch_first(ctx, st, fp, v));
                 B200_CUDA(cudaEventRecord(a->chain, st));
             }
+            continue;
+        }
+        if (a->op == B200_AGG_NUNIQUE) {
+            B200_CHECK(bin_nunique(ctx, sl, a, db, nbinners, stg.dev(aggs[k].data), static_cast<const uint8_t *>(stg.dev(aggs[k].mask)),
+                                   static_cast<const uint8_t *>(stg.dev(aggs[k].order)), nrows, vec));
             continue;
         }
         DevAgg &d = p.a[p.na++];

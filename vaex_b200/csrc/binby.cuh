@@ -81,7 +81,24 @@ struct FastParams {
 // tilesort.cu: rows sorted by grid region first, so that the scatter works on an L2-resident part of the grids
 int try_launch_tilesort(b200_ctx *ctx, Slot *slot, const FastParams &p, int xdtype, int nd, int vdtype, bool *taken);
 
+// NUNIQUE (nunique.cu)
+struct NUniqueParams {
+    int nb;
+    long long row0, nrows;
+    DevBinner b[B200_MAX_BINNERS];
+    int dtype, isz, byteswap;
+    const void *data;
+    const uint8_t *valid;      // 1 = value present (nullable)
+    const uint8_t *selection;  // 1 = row takes part (nullable)
+    unsigned long long *table; // 2 u64 per slot: {cell, canonical value bits}; empty = {~0, ~0}
+    unsigned long long tmask;
+    unsigned long long *distinct, *nan_rows, *null_rows; // cells each
+    unsigned long long *total;
+};
+
 int launch_binby(b200_ctx *ctx, Slot *slot, const BinParams &p, bool vec);
+int launch_nunique(b200_ctx *ctx, cudaStream_t stream, const NUniqueParams &p, bool vec);
+int launch_nunique_rehash(cudaStream_t stream, const unsigned long long *old_table, unsigned long long old_cap, unsigned long long *table, unsigned long long cap);
 int launch_first(b200_ctx *ctx, cudaStream_t stream, const FirstParams &p, bool vec);
 int launch_fill(cudaStream_t stream, void *ptr, int cell_dtype, uint64_t cells, uint64_t bits);
 int launch_merge(cudaStream_t stream, int op, int cell_dtype, void *dst, const void *src, uint64_t cells);

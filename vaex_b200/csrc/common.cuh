@@ -102,6 +102,13 @@ struct b200_agg {
     uint8_t *cell_masked = nullptr; // FIRST/LAST
     cudaEvent_t chain = nullptr;    // FIRST/LAST: completion of the previous select+deposit pair on this grid (any slot)
     std::mutex chain_mu;
+    // NUNIQUE: `grid` holds three planes of `cells` u64 (distinct pairs, NaN rows, null rows); the distinct (cell, value) pairs
+    // live in one open-addressing table of 16-byte slots
+    unsigned long long *ntable = nullptr;
+    uint64_t ncap = 0;                     // slots (power of two)
+    unsigned long long *ntotal = nullptr;  // device counter: pairs in the table
+    uint64_t npairs = 0;                   // host copy, refreshed after every launch
+    std::mutex nmu;                        // growth needs the table to itself
 };
 
 namespace b200 {

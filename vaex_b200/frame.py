@@ -153,6 +153,10 @@ class Frame:
     def last(self, expression, order_expression=None, binby=None, limits=None, shape=128, selection=None, edges=False):
         return self._agg(_agg.last(expression, order_expression), binby, limits, shape, selection, edges)
 
+    def nunique(self, expression, binby=None, limits=None, shape=128, selection=None, edges=False, dropna=False, dropnan=False, dropmissing=False):
+        """df.nunique (vaex/dataframe.py nunique -> agg.nunique -> AggNUnique_<dtype>, src/agg_nunique.cpp)."""
+        return self._agg(_agg.nunique(expression, dropna=dropna, dropnan=dropnan, dropmissing=dropmissing), binby, limits, shape, selection, edges)
+
     def _as_float64(self, expression):
         """var/std/skew/kurtosis run on ``expression.astype('float64')`` in the reference (vaex/agg.py:429-431)."""
         col = self.columns[expression]

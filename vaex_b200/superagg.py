@@ -234,6 +234,8 @@ class Aggregator:
             moment = int(extra[0])
         if op == _lib.AGG_FIRST and extra and extra[0]:
             op = _lib.AGG_LAST
+        if op == _lib.AGG_NUNIQUE:  # (dropmissing, dropnan) (src/agg_nunique.cpp:14)
+            moment = int(bool(extra[0])) | (int(bool(extra[1])) << 1)
         self._h = C.c_void_p()
         _lib.check(_lib.lib().b200_agg_create(self._ctx._h, op, self._code, _lib.DTYPE_CODE[self._dtype2], int(self._non_native), moment, len(grid),
                                               C.byref(self._h)))
@@ -374,6 +376,39 @@ class Aggregator:
         return keep
 
 
+class _AggNUnique(Aggregator):
+    """``AggNUnique_<dtype>(grid, grids, threads, dropmissing, dropnan)`` (src/agg_nunique.cpp:7-92, bound at :200-211): number of
+    distinct values per cell.  ``set_data_mask``: 0 = the row is null; ``set_selection_mask``: 0 = the row is skipped."""
+    _op = _lib.AGG_NUNIQUE
+
+    def __init__(self, grid, grids, threads, dropmissing, dropnan):
+        self._selection = {}
+        super().__init__(grid, grids, threads, dropmissing, dropnan)
+
+    def set_selection_mask(self, thread, ar):
+        self._selection[int(thread)] = _lib.mask_column(ar)
+
+    def clear_selection_mask(self, thread):
+        self._selection.pop(int(thread), None)
+
+    def get_result(self):
+        if self.grids != 1:
+            raise RuntimeError("Expected 1 grid")  # src/agg_nunique.cpp:20-22
+        return super().get_result()
+
+    def merge(self, others):
+        if others:
+            raise RuntimeError("merge not implemented")  # src/agg_nunique.cpp:43-46
+
+    def _fill(self, a, thread):
+        keep = super()._fill(a, thread)
+        s = self._selection.get(thread)
+        if s is not None:
+            a.order = s.ptr  # the C ABI carries the selection mask of NUNIQUE in the `order` slot (include/b200agg.h)
+            keep.append(s)
+        return keep
+
+
 def _make(name, base, **attrs):
     cls = type(name, (base,), attrs)
     cls.__module__ = __name__
@@ -394,10 +429,11 @@ for _name in _DT:
             _make("BinnerHash_" + _sfx, _BinnerHash, **_common)
         for _prefix, _op in _AGG_OPS.items():
             _make(_prefix + "_" + _sfx, Aggregator, _op=_op, **_common)
+        _make("AggNUnique_" + _sfx, _AggNUnique, **_common)
         for _name2 in _DT:
             _make("AggFirst_" + _name + "_" + _name2 + ("_non_native" if _nn else ""), Aggregator, _op=_lib.AGG_FIRST, _dtype2=_name2, **_common)
 
-# names the B200 path does not provide: nunique / list / string / object aggregators and BinnerCombined
+# names the B200 path does not provide: list / string / object aggregators (incl. AggNUnique_string) and BinnerCombined
 # (out of scope).  Accessing them raises instead of silently doing something else.
 _UNSUPPORTED_PREFIXES = ("AggNUnique_", "AggList_", "AggCount_string", "AggCount_object", "BinnerCombined")
 

@@ -137,6 +137,11 @@ class TaskPartAggregation(TaskPart):
                         selection_mask = np.asarray(selection_mask)
                         if np.ma.isMaskedArray(selection_mask):  # vaex.utils.unmask_selection_mask
                             selection_mask = selection_mask.data & ~np.ma.getmaskarray(selection_mask)
+                    # some aggregators make a distinction between missing value and no value (nunique): vaex/cpu.py:750-756
+                    if hasattr(op, "set_selection_mask"):
+                        op.set_selection_mask(thread_index, selection_mask)
+                elif hasattr(op, "clear_selection_mask"):
+                    op.clear_selection_mask(thread_index)
                 selection_index_global += 1
                 for i, expression in enumerate(agg_desc.expressions):
                     data, mask = split(block_map[expression])
