@@ -137,7 +137,8 @@ int b200_agg_read_on(b200_agg *agg, int slot, void *values_out);
 uint64_t b200_agg_cells(const b200_agg *agg);
 int b200_agg_result_dtype(const b200_agg *agg); /* count: I64; sum: upcast; min/max/first: dtype */
 size_t b200_agg_bytes(const b200_agg *agg);     /* sizeof(result dtype) * cells — the reference's bytes_used() for grids == 1 */
-/* which: 0 = primary device grid (cell type b200_agg_device_dtype), 1 = first/last packed {key,row} state */
+/* which: 0 = primary device grid (cell type b200_agg_device_dtype; NUNIQUE: its three u64 planes), 1 = first/last packed
+   {order key, global row} state (2 x u64 per cell), 2 = first/last order values (dtype2), 3 = first/last cell_masked (u8) */
 int b200_agg_device_ptr(b200_agg *agg, int which, void **ptr, size_t *bytes);
 int b200_agg_device_dtype(const b200_agg *agg);
 /* D2H of the finished grid in result dtype; `cell_masked` (nullable) is filled for FIRST/LAST (1 = empty cell) */

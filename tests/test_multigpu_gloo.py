@@ -125,3 +125,64 @@ def test_two_rank_groupby_key_union_gives_identical_ordinals(tmp_path):
     for key, c in zip(k0, counts):
         want = np.isnan(keys).sum() if key != key else (keys == key).sum()
         assert c == want
+
+
+def _local_first_state(idx, cells, order, row0, v, last):
+    """per-cell winner of one shard, the way csrc/first.cu keeps it: key = order as u64 bits with the sign flipped (LAST: its
+    complement), row = global row index; lexicographic minimum wins"""
+    key = (order.astype(np.int64).view(np.uint64) ^ np.uint64(1 << 63))
+    if last:
+        key = ~key
+    rows = (row0 + np.arange(len(idx))).astype(np.uint64)
+    best_key = np.full(cells, np.iinfo(np.uint64).max, np.uint64)
+    best_row = np.full(cells, np.iinfo(np.uint64).max, np.uint64)
+    value = np.full(cells, 99.0)
+    ordv = np.zeros(cells, np.int64)
+    masked = np.ones(cells, np.int8)
+    for j in np.lexsort((rows, key))[::-1]:  # worst first, so the best row of a cell is written last
+        c = int(idx[j])
+        best_key[c], best_row[c], value[c], ordv[c], masked[c] = key[j], rows[j], v[j], order[j], 0
+    return best_key, best_row, value, ordv, masked
+
+
+def _worker_first(rank, world, port, n, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    from vaex_b200 import engine
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0, 10, n)
+    v = rng.normal(0, 1, n)
+    t = rng.integers(-20, 20, n).astype("i8")  # many ties inside and across shards: the global row breaks them
+    i1, i2 = engine.shard_range(n, rank, world)
+    idx, shapes = O.flat_indices([O.scalar(x[i1:i2], 0, 10, 40)], i2 - i1)
+    for last in (False, True):
+        key, row, value, ordv, masked = _local_first_state(idx, shapes[0], t[i1:i2], i1, v[i1:i2], last)
+        tk, tr = torch.from_numpy(key.view(np.int64).copy()), torch.from_numpy(row.view(np.int64).copy())
+        tv, to, tm = torch.from_numpy(value.view(np.int64).copy()), torch.from_numpy(ordv.copy()), torch.from_numpy(masked.copy())
+        engine.all_reduce_first_tensors(tk, tr, tv, to, tm)
+        if rank == 0:
+            np.savez(os.path.join(out_dir, f"first_{int(last)}.npz"), value=tv.numpy().view(np.float64), order=to.numpy(), masked=tm.numpy(), row=tr.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_three_rank_first_last_reduction_matches_single_pass(tmp_path):
+    """first / last across row shards: MIN all-reduces on the packed (order key, global row) state + an owner-only
+    SUM of the value bits give exactly the single-pass result of the oracle, ties across shards included"""
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    n, world = 5_000, 3
+    mp.spawn(_worker_first, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0, 10, n)
+    v = rng.normal(0, 1, n)
+    t = rng.integers(-20, 20, n).astype("i8")
+    want_first, want_last = O.binby([O.scalar(x, 0, 10, 40)], [O.agg("first", v, order=t), O.agg("last", v, order=t)], n)
+    for last, want in ((0, want_first), (1, want_last)):
+        z = np.load(tmp_path / f"first_{last}.npz")
+        assert np.array_equal(z["masked"].astype(bool), np.ma.getmaskarray(want))
+        ok = ~np.ma.getmaskarray(want)
+        assert np.array_equal(z["value"][ok], np.asarray(want.data)[ok])

@@ -425,19 +425,31 @@ size_t b200_agg_bytes(const b200_agg *a) { return (size_t)dtype_size(b200_agg_re
 int b200_agg_device_dtype(const b200_agg *a) { return a->cell_dtype; }
 
 int b200_agg_device_ptr(b200_agg *a, int which, void **ptr, size_t *bytes) {
-    if (!a || !ptr || which < 0 || which > 1) {
+    if (!a || !ptr || which < 0 || which > 3) {
         set_error("b200_agg_device_ptr: invalid argument");
         return B200_ERR_INVALID;
     }
-    if (which == 0) {
+    size_t n = 0;
+    switch (which) {
+    case 0:
         *ptr = a->grid;
-        if (bytes)
-            *bytes = a->cells * dtype_size(a->cell_dtype);
-    } else {
+        n = a->cells * dtype_size(a->cell_dtype) * (a->op == B200_AGG_NUNIQUE ? 3 : 1);
+        break;
+    case 1:
         *ptr = a->state;
-        if (bytes)
-            *bytes = a->state ? a->cells * 16 : 0;
+        n = a->state ? a->cells * 16 : 0;
+        break;
+    case 2:
+        *ptr = a->order;
+        n = a->order ? a->cells * dtype_size(a->dtype2) : 0;
+        break;
+    default:
+        *ptr = a->cell_masked;
+        n = a->cell_masked ? a->cells : 0;
+        break;
     }
+    if (bytes)
+        *bytes = n;
     return B200_OK;
 }
 

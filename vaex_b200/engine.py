@@ -62,15 +62,86 @@ def all_reduce_tensor(t, op, unsigned_as_signed=False, group=None):
         else:
             dist.all_reduce(t, op=rop, group=group)
     elif op in (_lib.AGG_FIRST, _lib.AGG_LAST):
-        raise NotImplementedError("first/last across GPUs: reduce (key,row) states with b200_agg_merge on one rank")
+        raise NotImplementedError("first/last grids are reduced with all_reduce_first (key/row state, not the value grid)")
+    elif op == _lib.AGG_NUNIQUE:
+        raise NotImplementedError("nunique grids cannot be merged (the reference cannot either: src/agg_nunique.cpp:43-46)")
     else:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
 
 
+_SIGN = -(1 << 63)
+
+
+def all_reduce_first_tensors(key, row, value, order, masked, group=None):
+    """first/last across row shards: every rank holds, per cell, the packed winner of ITS rows — `key` (the order
+    key as u64 bits, smaller wins; LAST stores the complement), `row` (global row index, the tie-break), the winner's `value`
+    and `order` bits (int64 tensors) and `masked` (1 = no row of this rank fell into the cell).  Three MIN all-reduces find
+    the global (key, row) winner, which exactly one rank owns (rows are globally unique); that rank alone contributes its
+    value / order bits to two SUM all-reduces.  All tensors are updated in place; works on any backend (gloo in the CPU test)."""
+    import torch
+    import torch.distributed as dist
+    imax = torch.iinfo(torch.int64).max
+    gmask = masked.to(torch.int32)
+    dist.all_reduce(gmask, op=dist.ReduceOp.MIN, group=group)
+    has = masked == 0
+    k = torch.where(has, key ^ _SIGN, torch.full_like(key, imax))  # u64 order through a signed view: flip the sign bit
+    gk = k.clone()
+    dist.all_reduce(gk, op=dist.ReduceOp.MIN, group=group)
+    r = torch.where(has & (k == gk), row, torch.full_like(row, imax))
+    gr = r.clone()
+    dist.all_reduce(gr, op=dist.ReduceOp.MIN, group=group)
+    owner = has & (k == gk) & (r == gr)
+    gv = torch.where(owner, value, torch.zeros_like(value))
+    go = torch.where(owner, order, torch.zeros_like(order))
+    dist.all_reduce(gv, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(go, op=dist.ReduceOp.SUM, group=group)
+    any_has = gmask == 0
+    key.copy_(torch.where(any_has, gk ^ _SIGN, key))
+    row.copy_(torch.where(any_has, gr, row))
+    value.copy_(torch.where(any_has, gv, value))
+    order.copy_(torch.where(any_has, go, order))
+    masked.copy_(gmask.to(masked.dtype))
+
+
+def _raw_tensor(agg, which, np_dtype):
+    """flat torch view of one of the aggregator's device buffers, as the SIGNED integer type of the same width"""
+    import torch
+    ptr, nbytes = agg.device_pointer(which)
+    isz = np.dtype(np_dtype).itemsize
+
+    class V:
+        pass
+    v = V()
+    v.__cuda_array_interface__ = {"shape": (nbytes // isz,), "typestr": "<i%d" % isz if isz > 1 else "|i1", "data": (ptr, False), "version": 3, "strides": None}
+    v._keep = agg
+    t = torch.as_tensor(v, device=f"cuda:{agg._ctx.device}")
+    t._b200_keepalive = v
+    return t
+
+
+def all_reduce_first(agg, slot=0, group=None):
+    """In-place cross-rank reduction of a first/last aggregator (value grid, order grid, {key,row} state, cell_masked)."""
+    import torch
+    with torch.cuda.stream(slot_stream(agg._ctx, slot)):
+        state = _raw_tensor(agg, 1, "int64").view(-1, 2)
+        vraw = _raw_tensor(agg, 0, agg.device_dtype)
+        oraw = _raw_tensor(agg, 2, agg._dtype2)
+        masked = _raw_tensor(agg, 3, "int8")
+        key, row = state[:, 0].contiguous(), state[:, 1].contiguous()
+        value, order = vraw.to(torch.int64), oraw.to(torch.int64)
+        all_reduce_first_tensors(key, row, value, order, masked, group)
+        state[:, 0].copy_(key)
+        state[:, 1].copy_(row)
+        vraw.copy_(value.to(vraw.dtype))
+        oraw.copy_(order.to(oraw.dtype))
+
+
 def all_reduce_agg(agg, slot=0, group=None):
     """In-place all-reduce of one aggregator's device grid across the ranks of `group` (ordered after the slot's kernels)."""
     import torch
+    if agg._op in (_lib.AGG_FIRST, _lib.AGG_LAST) or getattr(agg, "_is_first", False):
+        return all_reduce_first(agg, slot, group)
     t, signed_view = grid_tensor(agg)
     with torch.cuda.stream(slot_stream(agg._ctx, slot)):
         all_reduce_tensor(t, agg._op, signed_view, group)
