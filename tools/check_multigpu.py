@@ -52,7 +52,7 @@ def main():
     for a in aggs[4:6]:
         a.set_data(0, dv, 0)
         a.set_data(0, dt, 1)
-    aggs[6].set_data(0, dv, 0)  # no order column: the global row index orders the rows
+    aggs[6].set_data(0, dv, 0)  # no order column: the chunk-local row orders the rows, the global row breaks ties
     grid.bin(0, aggs, i2 - i1, row_offset=i1)
     if world > 1:
         engine.all_reduce(aggs)

@@ -13,7 +13,8 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200agg.so")
+# VAEX_B200_LIB: load this build of the library instead of the in-tree one (A/B timing of kernel variants on one box)
+LIB_PATH = os.environ.get("VAEX_B200_LIB") or os.path.join(_HERE, "libb200agg.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["api.cu", "binby.cu", "fast.cu", "first.cu", "hashset.cu", "nunique.cu", "tilecount.cu", "tilesort.cu"]
 
