@@ -158,6 +158,49 @@ def main():
             report("C4/pass2", "groupby sum+count through the fused hash binner (probe + 2 REDs per row)", n, 16, ms2, unique_keys=nkeys)
             report("C4/total", "df.groupby(k).agg({v:[sum,count]}) both passes", n, 24, t_pass1b * 1e3 + ms2, unique_keys=nkeys)
             del keys, v
+        elif cfg == "NU":
+            # per-cell nunique: 64 cells, values drawn from 1e5 / 1e7 distinct ints -> 5e6 / ~1e8-pair tables
+            for card in (100_000, 10_000_000):
+                gcol = torch.randint(0, 64, (n,), device="cuda", dtype=torch.int32, generator=gen)
+                v = torch.randint(0, card, (n,), device="cuda", dtype=torch.int64, generator=gen)
+                torch.cuda.synchronize()
+                bo = superagg.BinnerOrdinal_int32(1, "g", 64, 0, False, False)
+                g = superagg.Grid([bo])
+                bo.set_data(0, gcol)
+                a = superagg.AggNUnique_int64(g, 1, 1, False, False)
+                a.set_data(0, v, 0)
+                t0 = time.perf_counter()
+                g.bin(0, [a], n)
+                ctx.sync()
+                t_first = time.perf_counter() - t0
+                pairs = int(a.get_result().sum())
+                t0 = time.perf_counter()
+                g.bin(0, [a], n)  # same rows again: every pair is found, nothing is inserted, the table does not grow
+                ctx.sync()
+                t_again = time.perf_counter() - t0
+                assert int(a.get_result().sum()) == pairs
+                report(f"NU/{card}", "nunique(v) binby 64 ordinal cells, int64 values (first pass incl. table growth; second pass = lookups only)", n, 12,
+                       t_first * 1e3, distinct_pairs=pairs, lookups_only_ms=t_again * 1e3)
+                del gcol, v, a
+        elif cfg == "SG":
+            # sparse two-key groupby: 3000 x 3000 possible combinations, sum + count of v
+            from vaex_b200.frame import Frame
+            k1 = torch.randint(0, 3000, (n,), device="cuda", dtype=torch.int64, generator=gen) * 1000 + 7
+            k2 = torch.randint(0, 3000, (n,), device="cuda", dtype=torch.int64, generator=gen)
+            v = torch.empty(n, dtype=torch.float64, device="cuda").normal_(generator=gen)
+            torch.cuda.synchronize()
+            df = Frame(dict(k1=k1, k2=k2, v=v))
+            t0 = time.perf_counter()
+            gb = df.groupby(["k1", "k2"], combine=True)
+            ctx.sync()
+            t_keys = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            out = gb.agg({"v": ["sum", "count"]})
+            t_agg = time.perf_counter() - t0
+            assert int(out["count"].sum()) == n
+            report("SG", "df.groupby([k1,k2], combine=True).agg({v:[sum,count]}): 2 key sets + combined-code set, then fused probe pass", n, 24 + 24,
+                   (t_keys + t_agg) * 1e3, groups=len(out["count"]), key_sets_ms=t_keys * 1e3, aggregate_ms=t_agg * 1e3)
+            del k1, k2, v
 
 
 if __name__ == "__main__":
