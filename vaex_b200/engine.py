@@ -140,7 +140,7 @@ def all_reduce_first(agg, slot=0, group=None):
 def all_reduce_agg(agg, slot=0, group=None):
     """In-place all-reduce of one aggregator's device grid across the ranks of `group` (ordered after the slot's kernels)."""
     import torch
-    if agg._op in (_lib.AGG_FIRST, _lib.AGG_LAST) or getattr(agg, "_is_first", False):
+    if agg._op in (_lib.AGG_FIRST, _lib.AGG_LAST):  # superagg.AggFirst_* carry AGG_FIRST for both first and last
         return all_reduce_first(agg, slot, group)
     t, signed_view = grid_tensor(agg)
     with torch.cuda.stream(slot_stream(agg._ctx, slot)):
