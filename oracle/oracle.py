@@ -5,6 +5,11 @@ TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.
 
 The spec objects below (``scalar``, ``ordinal``, ``agg``) are plain dicts so that the very same specs
 can be handed to the product (vaex_b200) in the parity tests.
+
+Parity status: PINNED.  The C library is checked against the compiled reference and its known-answer vectors
+(tests/test_oracle_pinning.py); the two pieces restated in Python here — ``nunique`` (AggNUniquePrimitive) and
+``flat_indices`` — are pinned by the ``nunique_*`` golden vectors that tests/golden/make_golden.py produced with the
+compiled reference (incl. its -0.0 / row-count quirks).
 """
 import ctypes as C
 import os
