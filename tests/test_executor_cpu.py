@@ -1,0 +1,113 @@
+"""The chunk-feed loop (vaex_b200/execution.py, the restatement of ExecutorLocal: vaex/execution.py:385-455, 516-571 and the
+stable worker index of vaex/multithreading.py:64-80) exercised on the CPU with a recording task part — no device involved."""
+import threading
+
+import numpy as np
+import pytest
+
+
+class RecordingPart:
+    """duck-typed task part: what the executor needs is `expressions`, `process`, `reduce`, `get_result`, `stopped`"""
+
+    def __init__(self, expressions, fail_at=None, stop_after=None):
+        self.expressions = list(expressions)
+        self.calls = []
+        self.lock = threading.Lock()
+        self.stopped = False
+        self.fail_at = fail_at
+        self.stop_after = stop_after
+        self.reduced = False
+
+    def process(self, thread_index, i1, i2, filter_mask, selection_masks, blocks):
+        with self.lock:
+            self.calls.append((thread_index, threading.get_ident(), i1, i2, [len(b) for b in blocks], [None if s is None else len(s) for s in selection_masks],
+                               float(np.asarray(blocks[0], dtype="f8").sum())))
+            if self.fail_at is not None and i1 >= self.fail_at:
+                raise ValueError("boom")
+            if self.stop_after is not None and len(self.calls) >= self.stop_after:
+                self.stopped = True
+
+    def reduce(self, others):
+        self.reduced = True
+
+    def get_result(self):
+        return sorted((c[2], c[3]) for c in self.calls)
+
+
+def _run(n, nthreads, chunk, **kw):
+    from vaex_b200.execution import Executor, Task
+    cols = {"x": np.arange(n, dtype="f8"), "y": np.ones(n, dtype="i4")}
+    part = RecordingPart(["x", "y"], **kw)
+    sel = np.arange(n) % 2 == 0
+    ex = Executor(nthreads=nthreads, chunk_size=chunk)
+    return part, ex, ex.execute(cols, [Task(part, selections=[sel, None])], n)
+
+
+@pytest.mark.parametrize("nthreads,chunk", [(1, 7), (3, 7), (4, 1000), (2, None)])
+def test_every_row_is_fed_exactly_once_with_matching_blocks(nthreads, chunk):
+    n = 100
+    part, ex, (ranges,) = _run(n, nthreads, chunk)
+    assert part.reduced and ex.passes == 1
+    assert ranges[0][0] == 0 and ranges[-1][1] == n and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    for t, _, i1, i2, lens, sel_lens, s in part.calls:
+        assert 0 <= t < nthreads
+        assert lens == [i2 - i1, i2 - i1] and sel_lens == [i2 - i1, None]
+        assert s == float(np.arange(i1, i2).sum())  # the block really is rows [i1, i2)
+    if chunk == 7:
+        assert max(i2 - i1 for _, _, i1, i2, *_ in part.calls) == 7
+
+
+def test_worker_threads_keep_one_index_for_their_lifetime():
+    # ThreadPoolIndex (vaex/multithreading.py:64-80): thread_index selects the slot, so it must be stable per OS thread
+    part, _, _ = _run(5000, 4, 50)
+    by_thread = {}
+    for t, ident, *_ in part.calls:
+        by_thread.setdefault(ident, set()).add(t)
+    assert all(len(v) == 1 for v in by_thread.values())
+    assert len({next(iter(v)) for v in by_thread.values()}) == len(by_thread)  # and no two threads share one
+
+
+def test_exception_in_process_reaches_the_caller():
+    # vaex/execution.py:567-571: the first error rejects the task; the pass is not silently completed
+    with pytest.raises(ValueError, match="boom"):
+        _run(100, 3, 10, fail_at=50)
+
+
+def test_stopped_part_is_not_fed_again():
+    part, _, _ = _run(1000, 1, 10, stop_after=3)
+    assert len(part.calls) == 3
+
+
+def test_missing_column_and_empty_frame():
+    from vaex_b200.execution import Executor, Task
+    with pytest.raises(KeyError):
+        Executor(1).execute({"x": np.zeros(3)}, [Task(RecordingPart(["nope"]))], 3)
+    part = RecordingPart(["x"])
+    Executor(2).execute({"x": np.zeros(0)}, [Task(part)], 0)
+    assert part.calls == [] and part.reduced
+
+
+def test_device_virtual_columns_are_evaluated_per_chunk_on_the_workers_slot():
+    """hash.CombinedCodes protocol: the executor calls chunk(thread_index, i1, i2) instead of slicing"""
+    from vaex_b200.execution import Executor, Task
+
+    class Virtual:
+        device_virtual = True
+        columns = [np.zeros(4)]  # host inputs -> chunked feed
+        dtype = np.dtype("int64")
+
+        def __init__(self, n):
+            self.n, self.seen = n, []
+
+        def __len__(self):
+            return self.n
+
+        def chunk(self, thread_index, i1, i2):
+            self.seen.append((thread_index, i1, i2))
+            return np.arange(i1, i2, dtype="f8")
+
+    v = Virtual(40)
+    part = RecordingPart(["v"])
+    Executor(nthreads=1, chunk_size=16).execute({"v": v}, [Task(part)], 40)
+    assert [(a, b) for _, a, b in v.seen] == [(0, 16), (16, 32), (32, 40)]
+    assert [c[6] for c in part.calls] == [float(np.arange(a, b).sum()) for _, a, b in v.seen]
