@@ -136,9 +136,9 @@ def test_headline_shape_sample(oracle):
 
 
 def test_tile_partitioned_count_matches_oracle(oracle):
-    """count(*) on big grids takes the two-kernel tile-partition path (csrc/tilecount.cu) from 2^22 rows on: check it
-    against the oracle for fp32 2-D 1024^2 (33 grid tiles), fp64 3-D 126^3 (65 tiles) and a degenerate distribution that
-    overflows its bucket (falls back to direct REDs for the excess)."""
+    """count(*) on big grids takes the two-kernel partition path (csrc/ringcount.cu) from 2^22 rows on: check it against the
+    oracle for fp32 2-D 1024^2 (32 parts), fp64 3-D 126^3 (64 parts) and a degenerate distribution (one hot cell: the ring of
+    its part overflows in every group and the excess rows go to direct REDs)."""
     rng = np.random.default_rng(21)
     n = (1 << 22) + 12345
     x, y = (rng.normal(0, 1, n).astype("f4") for _ in range(2))
@@ -155,6 +155,45 @@ def test_tile_partitioned_count_matches_oracle(oracle):
     b = [oracle.scalar(x, -3, 3, 1024), oracle.scalar(y, -3, 3, 1024)]
     got = b200_binby(b, [oracle.agg("count")], n, device=True)[0]
     assert np.array_equal(oracle.binby(b, [oracle.agg("count")], n)[0], got) and int(got.sum()) == n
+
+
+@pytest.mark.parametrize("case", ["2d_f32_sorted_keys", "1d_f64_64parts", "3d_f32_128parts", "2d_f64_two_hot_parts", "2d_f32_all_nan_y", "2d_f32_ragged"])
+def test_ring_partition_variants(case, oracle):
+    """csrc/ringcount.cu over its template space (fp32 / fp64 keys, 1-3 dimensions, 32 / 64 / 128 parts) and the distributions
+    that stress the rings and the chunk lists: keys sorted by the partitioning dimension (every warp fills ONE ring: overflow ->
+    direct REDs), two hot parts, a column of NaN (everything in cell row 0), a row count that is no multiple of anything."""
+    rng = np.random.default_rng(77)
+    n = (1 << 22) + 4097
+    if case == "2d_f32_sorted_keys":
+        x = rng.normal(0, 1, n).astype("f4")
+        y = np.sort(rng.normal(0, 1, n)).astype("f4")
+        b = [oracle.scalar(x, -3, 3, 1024), oracle.scalar(y, -3, 3, 1024)]
+    elif case == "1d_f64_64parts":
+        x = rng.normal(0, 1, n)
+        x[::9973] = np.nan
+        b = [oracle.scalar(x, -4, 4, 3_000_000)]  # 3,000,003 cells -> 64 parts
+    elif case == "3d_f32_128parts":
+        x, y, z = (rng.uniform(-1, 1, n).astype("f4") for _ in range(3))
+        b = [oracle.scalar(x, -1, 1, 157), oracle.scalar(y, -0.9, 1, 157), oracle.scalar(z, -1, 0.9, 157)]  # 160^3 = 4.096M: >= 2^22 cells, direct path
+        got = b200_binby(b, [oracle.agg("count")], n, device=True)[0]
+        assert np.array_equal(oracle.binby(b, [oracle.agg("count")], n)[0], got)
+        b = [oracle.scalar(x, -1, 1, 150), oracle.scalar(y, -0.9, 1, 150), oracle.scalar(z, -1, 0.9, 150)]  # 153^3 = 3.58M cells -> 128 parts
+    elif case == "2d_f64_two_hot_parts":
+        x = rng.normal(0, 1, n)
+        y = np.where(rng.random(n) < 0.5, 0.001, 2.5) + rng.normal(0, 1e-3, n)
+        b = [oracle.scalar(x, -3, 3, 700), oracle.scalar(y, -3, 3, 900)]
+    elif case == "2d_f32_all_nan_y":
+        x = rng.normal(0, 1, n).astype("f4")
+        y = np.full(n, np.nan, "f4")
+        y[: n // 16] = rng.normal(0, 1, n // 16).astype("f4")
+        b = [oracle.scalar(x, -3, 3, 1024), oracle.scalar(y, -3, 3, 1024)]
+    else:
+        n = (1 << 23) + 255
+        x, y = (rng.standard_t(2, n).astype("f4") for _ in range(2))  # heavy tails: both edge cells busy
+        b = [oracle.scalar(x, -3, 3, 2000), oracle.scalar(y, -3, 3, 500)]
+    want = oracle.binby(b, [oracle.agg("count")], n)[0]
+    got = b200_binby(b, [oracle.agg("count")], n, device=True)[0]
+    assert np.array_equal(want, got) and int(got.sum()) == n
 
 
 def test_grid_larger_than_l2_matches_oracle(oracle):

@@ -45,10 +45,13 @@ def main():
         ctx.sync()
         if rep >= 3:
             times.append(e0.elapsed_time(e1))
-    total = int(agg.get_result().sum())
+    res = agg.get_result()
+    total = int(res.sum())
+    import hashlib
+    sha = hashlib.sha1(res.tobytes()).hexdigest()[:16]
     times.sort()
-    print(json.dumps({"tag": args.tag, "lib": os.path.basename(_lib.LIB_PATH), "prefetch": os.environ.get("B200_TILE_PREFETCH"), "rows": n,
-                      "ms_min": times[0], "ms_median": times[len(times) // 2], "rows_per_s_median": n / (times[len(times) // 2] * 1e-3), "count_ok": total == n}))
+    print(json.dumps({"tag": args.tag, "lib": os.path.basename(_lib.LIB_PATH), "path": os.environ.get("B200_COUNT_PATH", "ring"), "fg": os.environ.get("B200_RING_FG"), "rows": n,
+                      "ms_min": times[0], "ms_median": times[len(times) // 2], "rows_per_s_median": n / (times[len(times) // 2] * 1e-3), "count_ok": total == n, "grid_sha": sha}))
 
 
 if __name__ == "__main__":

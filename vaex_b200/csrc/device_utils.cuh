@@ -134,6 +134,24 @@ __device__ __forceinline__ unsigned long long scalar_index(double v, bool masked
     return (unsigned long long)(long long)(__double2int_rz(__dmul_rn(scaled, bins_d)) + 2);
 }
 
+// The ONE branch-free form every specialised float kernel (fast.cu, ringcount.cu, tilesort.cu) uses; bit-identical to
+// scalar_index above for unmasked rows (tests/test_gpu_parity.py::test_bin_edges_bit_exact, test_bin_index_sweep_all_fp32).
+// Reference: nan -> 0; scaled < 0 -> 1; scaled >= 1 -> bins+2; else (int)(scaled*bins)+2.
+// With t = RN(scaled*bins): scaled < 0 <=> t < 0 and scaled >= 1 <=> t >= bins (RN is monotone, and for scaled < 1 the
+// product rounds to at most `bins`, which lands in the same cell bins+2), and floor(t) == trunc(t) on [0, bins).  So ONE
+// saturating round-down conversion + an integer clamp reproduce the three range branches; only NaN needs its own test.
+// Returns cell - 1 in [-1, bins+1] so that callers fold the "+1" into the constant sum(stride):
+//   clamp(i, -1, bins) + 1 == max(min(i, bins) + 1, 0): VIMNMX + VIADDMNMX (DPX), no overflow (min first).
+__device__ __forceinline__ int bin_cell_m1(double v, double vmin, double scale, double bins_d, unsigned bins) {
+    const double scaled = __dmul_rn(__dsub_rn(v, vmin), scale);
+    const int i = __double2int_rd(__dmul_rn(scaled, bins_d)); // saturates; NaN -> 0 (fixed up below)
+    const int c = __viaddmax_s32(min(i, (int)bins), 1, 0);
+    return scaled != scaled ? -1 : c;
+}
+__device__ __forceinline__ unsigned bin_index(double v, double vmin, double scale, double bins_d, unsigned bins) {
+    return (unsigned)(bin_cell_m1(v, vmin, scale, bins_d, bins) + 1);
+}
+
 // ---- BinnerOrdinal::to_bins (src/binner_ordinal.cpp:20-176) ---------------------------------------
 __device__ __forceinline__ long long ordinal_value(int dt, uint64_t r, long long min_value, bool flip) {
     long long value;

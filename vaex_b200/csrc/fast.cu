@@ -23,17 +23,6 @@ namespace {
 
 constexpr int kThreads = 256;
 
-// BinnerScalar::to_bins (src/binners.cpp:13-57), bit-exact, branch-light
-__device__ __forceinline__ unsigned bin_index(double v, double vmin, double scale, double bins_d, unsigned bins) {
-    // Reference: nan -> 0; scaled < 0 -> 1; scaled >= 1 -> bins+2; else (int)(scaled*bins)+2.
-    // With t = RN(scaled*bins): scaled < 0 <=> t < 0 and scaled >= 1 <=> t >= bins (RN is monotone, and for scaled < 1 the
-    // product rounds to at most the double below `bins`), and floor(t) == trunc(t) on [0, bins).  So ONE saturating
-    // round-down conversion + integer clamp reproduces all three range branches; only NaN needs its own test.
-    const double scaled = __dmul_rn(__dsub_rn(v, vmin), scale);
-    const int i = __double2int_rd(__dmul_rn(scaled, bins_d)); // saturates; NaN -> 0 (fixed up below)
-    const unsigned idx = (unsigned)(min(max(i, -1), (int)bins) + 2);
-    return scaled != scaled ? 0u : idx;
-}
 
 template <typename T>
 __device__ __forceinline__ double widen(T v);

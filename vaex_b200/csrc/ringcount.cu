@@ -1,0 +1,637 @@
+// ringcount.cu — count(*) on grids that do not fit in shared memory WITHOUT one L2 atomic per row (the headline path).
+//
+// Why two kernels: a direct kernel issues one RED per row, and the L2 retires only ~98 sector operations per clock chip-wide,
+// loads included (profiles/r01_ncu_fast.txt), which caps the 2-D 1024^2 count at ~1.5e11 rows/s = 18 % of the HBM stream rate.
+// Shared-memory atomics retire ~6 lanes/clk/SM, 9x more, but a 1027^2 grid is 4 MB even with 32-bit counters.  So the grid is
+// cut into <= 32 (else 64 / 128) GRID TILES ("parts") of <= 49152 consecutive cells and the rows are partitioned by part first:
+//
+//   K1 k_ring_partition  every WARP is autonomous.  Columns are staged by TMA (cp.async.bulk + mbarrier, double buffered).
+//                        Per row: the bit-exact fp64 bin index, part = idx / tile_cells (one IMAD.HI), ONE shared-memory atomic
+//                        on the (warp, part) counter whose return value is the row's slot in that part's RING, and one 16-bit
+//                        store of the local cell index into the ring.  Every 256 rows each lane — lane l OWNS part l — flushes
+//                        the complete 16-entry granules (one 32-byte sector each: two LDS.128 + two STG.128) of its ring to the
+//                        part's current CHUNK in global memory and moves the < 16 leftover entries to the ring's front.
+//                        There is no scan, no scatter pass and no copy-out pass: round 1's kernel spent 47 of its 77 warp
+//                        instructions per 32 rows there (profiles/r01_ncu_final_k1_phases.txt).
+//                        Chunks (512..2048 entries) come from ONE pool: a warp reserves 32 chunks with one global atomic and
+//                        hands them to its parts with a ballot; the chunks of a (warp, part) form a linked list (next[]), its
+//                        head and entry count go to head[] / len[].  No per-part bucket provisioning, no overflow fallback, and
+//                        2 B/row of scratch whatever the distribution.
+//   K2 k_ring_count      one persistent CTA per SM takes a contiguous share of the (part, warp) lists (balanced by entry count:
+//                        every warp sees the same row distribution), keeps the part's u32 histogram in <= 192 KB of shared
+//                        memory, walks the lists with 128-bit loads + one ATOMS per entry, and flushes the non-zero cells with one
+//                        RED.ADD.64 each when the part changes (1-2 flushes per CTA).
+//
+// HBM traffic: 8 B/row of columns + 2 B/row written + 2 B/row read.  Exact integer counts, same grid layout, any distribution:
+// a ring that fills up inside one 256-row group (> 48 rows of a warp in one part) sends the excess rows to direct REDs.
+#include <algorithm>
+
+#include "binby.cuh"
+#include "device_utils.cuh"
+
+namespace b200 {
+
+struct RingParams {
+    const void *x[3];
+    double vmin[3], scale[3], bins_d[3];
+    unsigned bins[3];
+    unsigned stride[3];
+    unsigned stride_sum;          // sum(stride): bin_cell_m1 returns cell - 1
+    long long row0, nrows;        // this batch
+    unsigned cells;
+    unsigned tile_cells;          // cells per part (<= 49151): part = idx / tile_cells, local = idx % tile_cells < 2^16
+    unsigned magic;               // part == __umulhi(idx, magic) for every idx < cells (verified on the host)
+    int nparts;
+    int nparts_pad;               // 32 * PPL
+    unsigned chunk_shift;         // chunk = 1 << chunk_shift entries (9..11)
+    unsigned nchunks_cap;         // chunks in the pool
+    unsigned nlists_w;            // warps of K1 (lists per part)
+    unsigned short *pool;         // chunk c = pool + (c << chunk_shift)
+    unsigned *next;               // per chunk: next chunk of the same (warp, part) list; kNone = last      (memset 0xFF)
+    unsigned short *unused;       // per chunk: entries at the tail that were never written                 (memset 0)
+    unsigned *head;               // [warp][nparts_pad]: first chunk of the list; kNone = empty               (memset 0xFF)
+    unsigned *len;                // [warp][nparts_pad]: entries in the list (pads included)                  (memset 0)
+    unsigned *ctl;                // [0] pool cursor in chunks                                                (memset 0)
+    unsigned long long *grid;
+};
+
+namespace {
+
+constexpr int kGroupRows = 256;   // rows between two ring flushes: 8 per lane
+constexpr int kGran = 16;         // entries per flush granule = one 32-byte sector
+constexpr unsigned kSuper = 32;   // chunks a warp reserves from the pool at a time
+constexpr unsigned kMaxTileCells = 49151; // 192 KB of u32 counters in k_ring_count, one of them the pad cell
+constexpr int kMaxParts = 128;
+constexpr unsigned kNone = 0xFFFFFFFFu;
+constexpr int kCountThreads = 1024;
+
+// ---- TMA staging (cp.async.bulk global -> shared, completion on an mbarrier): each warp keeps the NEXT tile's columns in
+// flight while it works on the current one.  No registers, no LSU issue slots, and the copy engine sees >= 1 KB requests.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile("{\n\t"
+                 ".reg .pred P1;\n\t"
+                 "RING_WAIT_LOOP:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+                 "@P1 bra RING_WAIT_DONE;\n\t"
+                 "bra RING_WAIT_LOOP;\n\t"
+                 "RING_WAIT_DONE:\n\t"
+                 "}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename T>
+__device__ __forceinline__ void lds4(const T *buf, int i, double out[4]);
+template <>
+__device__ __forceinline__ void lds4<float>(const float *buf, int i, double out[4]) {
+    const float4 a = *reinterpret_cast<const float4 *>(buf + i);
+    out[0] = (double)a.x, out[1] = (double)a.y, out[2] = (double)a.z, out[3] = (double)a.w;
+}
+template <>
+__device__ __forceinline__ void lds4<double>(const double *buf, int i, double out[4]) {
+    const double2 a = *reinterpret_cast<const double2 *>(buf + i), b = *reinterpret_cast<const double2 *>(buf + i + 2);
+    out[0] = a.x, out[1] = a.y, out[2] = b.x, out[3] = b.y;
+}
+template <typename T>
+__device__ __forceinline__ void ldg4(const void *p, long long i, double out[4]);
+template <>
+__device__ __forceinline__ void ldg4<float>(const void *p, long long i, double out[4]) {
+    const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(static_cast<const float *>(p) + i));
+    out[0] = (double)__uint_as_float(a.x), out[1] = (double)__uint_as_float(a.y), out[2] = (double)__uint_as_float(a.z), out[3] = (double)__uint_as_float(a.w);
+}
+template <>
+__device__ __forceinline__ void ldg4<double>(const void *p, long long i, double out[4]) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(static_cast<const double *>(p) + i);
+    const uint4 a = __ldcs(q), b = __ldcs(q + 1);
+    out[0] = __longlong_as_double(((long long)a.y << 32) | a.x), out[1] = __longlong_as_double(((long long)a.w << 32) | a.z);
+    out[2] = __longlong_as_double(((long long)b.y << 32) | b.x), out[3] = __longlong_as_double(((long long)b.w << 32) | b.z);
+}
+
+// one group of 256 rows (8 per lane): bit-exact index, part, ONE shared-memory atomic for the slot, one 16-bit store.
+// STAGED: the columns sit in shared memory (TMA), every row exists.  Otherwise: global loads with bounds (the ragged last tile).
+template <typename T, int ND, int RING, int RSTRIDE, bool STAGED>
+__device__ __forceinline__ void group_rows(const RingParams &p, const T *buf, int col_stride, long long gbase, long long tend, int lane, unsigned *cnt,
+                                           unsigned short *ring, unsigned idx[8], unsigned &ovf) {
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        double c[ND][4];
+        const int r0 = q * 128 + lane * 4;
+        if (STAGED) {
+#pragma unroll
+            for (int d = 0; d < ND; d++)
+                lds4<T>(buf + d * col_stride, r0, c[d]);
+        } else if (gbase + r0 + 4 <= tend) {
+#pragma unroll
+            for (int d = 0; d < ND; d++)
+                ldg4<T>(p.x[d], gbase + r0, c[d]);
+        } else {
+#pragma unroll
+            for (int d = 0; d < ND; d++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    c[d][j] = gbase + r0 + j < tend ? (double)__ldcs(static_cast<const T *>(p.x[d]) + gbase + r0 + j) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            unsigned id = p.stride_sum;
+#pragma unroll
+            for (int d = 0; d < ND; d++)
+                id += (unsigned)bin_cell_m1(c[d][j], p.vmin[d], p.scale[d], p.bins_d[d], p.bins[d]) * p.stride[d];
+            idx[q * 4 + j] = id;
+            if (STAGED || gbase + r0 + j < tend) {
+                const unsigned part = __umulhi(id, p.magic);
+                const unsigned slot = atomicAdd(cnt + part, 1u);
+                if (slot < (unsigned)RING)
+                    ring[part * RSTRIDE + slot] = (unsigned short)(id - part * p.tile_cells);
+                else
+                    ovf |= 1u << (q * 4 + j);
+            }
+        }
+    }
+}
+
+// shared memory of one warp: [2 stages x ND columns x TILE rows of T] [rings: 32*PPL parts x RING u16] [counters: 32*PPL u32]
+template <typename T, int ND, int PPL, int FG>
+struct RingLayout {
+    static constexpr int kTileRows = kGroupRows * FG;
+    static constexpr int kRing = PPL <= 2 ? 64 : 32; // ring entries per part: < 16 left over + up to RING-15 new ones per group
+    static constexpr size_t kColBytes = 2ull * ND * kTileRows * sizeof(T);
+    // rows of RING + 8 entries: the 16-byte pad rotates consecutive parts over the banks, so the owners' LDS.128 / STS.128 of a
+    // flush (lane l -> row l) do not all hit banks 0-3
+    static constexpr int kRingStride = kRing + 8;
+    static constexpr size_t kRingBytes = 32ull * PPL * kRingStride * 2;
+    static constexpr size_t kCntBytes = 32ull * PPL * 4;
+    static constexpr size_t kPerWarp = kColBytes + kRingBytes + kCntBytes;
+};
+
+// state of the parts a lane owns (parts lane, lane+32, ...): where the next granule goes
+template <int PPL>
+struct Owner {
+    unsigned wpos[PPL]; // next entry to write (pool entry index); == wend: the current chunk is full / there is none yet
+    unsigned wend[PPL];
+    unsigned cur[PPL];  // current chunk id (kNone: none yet)
+    unsigned total[PPL]; // entries written to this list so far
+};
+
+template <typename T, int ND, int PPL, int FG, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2) k_ring_partition(const __grid_constant__ RingParams p) {
+    using L = RingLayout<T, ND, PPL, FG>;
+    constexpr int RING = L::kRing, RSTRIDE = L::kRingStride;
+    constexpr int TILE = L::kTileRows;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ __align__(8) unsigned long long bars[WARPS][2];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *mine = dyn_smem + (size_t)warp * L::kPerWarp;
+    T *const cols = reinterpret_cast<T *>(mine);                                         // [2][ND][TILE]
+    unsigned short *const ring = reinterpret_cast<unsigned short *>(mine + L::kColBytes); // [32*PPL][RING + 8]
+    unsigned *const cnt = reinterpret_cast<unsigned *>(mine + L::kColBytes + L::kRingBytes);
+    if (lane == 0) {
+        mbar_init(&bars[warp][0], 1);
+        mbar_init(&bars[warp][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#pragma unroll
+    for (int k = 0; k < PPL; k++)
+        cnt[lane + 32 * k] = 0;
+    __syncwarp();
+
+    const int nparts = p.nparts;
+    const unsigned cshift = p.chunk_shift, csize = 1u << cshift;
+    const long long ntiles = (p.nrows + TILE - 1) / TILE;
+    const long long nfull = p.nrows / TILE; // tiles [0, nfull) are complete (and TMA staged)
+    const long long wglobal = (long long)blockIdx.x * WARPS + warp, wtotal = (long long)gridDim.x * WARPS;
+
+    Owner<PPL> own;
+#pragma unroll
+    for (int k = 0; k < PPL; k++)
+        own.wpos[k] = own.wend[k] = 0, own.cur[k] = kNone, own.total[k] = 0;
+    // the warp's reservation in the pool: chunks [sc_next, sc_end) are free; lane 0 holds the NEXT reservation (prefetched)
+    unsigned sc_next = 0, sc_end = 0, sn_pref = 0;
+    if (lane == 0)
+        sn_pref = atomicAdd(p.ctl, kSuper);
+
+    auto issue = [&](long long t, int st) { // lane 0: start the bulk copies of tile t's columns into stage st
+        mbar_expect_tx(&bars[warp][st], (unsigned)(ND * TILE * sizeof(T)));
+#pragma unroll
+        for (int d = 0; d < ND; d++)
+            tma_load_1d(cols + (st * ND + d) * TILE, static_cast<const T *>(p.x[d]) + p.row0 + t * TILE, (unsigned)(TILE * sizeof(T)), &bars[warp][st]);
+    };
+
+    // ---- flush: every lane appends the complete granules of the rings it owns to their chunk lists -----------------------------
+    // `final`: also the incomplete last granule, padded with entries == tile_cells (the pad cell of k_ring_count)
+    auto flush = [&](bool final) {
+        unsigned n[PPL], ngran[PPL];
+        bool need[PPL];
+#pragma unroll
+        for (int k = 0; k < PPL; k++) {
+            const int part = lane + 32 * k;
+            n[k] = min(cnt[part], (unsigned)RING); // rows past RING went to direct REDs (`ovf` below)
+            if (final && (n[k] & (kGran - 1))) {
+                for (unsigned e = n[k]; e < ((n[k] + kGran - 1) & ~(kGran - 1)); e++)
+                    ring[part * RSTRIDE + e] = (unsigned short)p.tile_cells;
+                n[k] = (n[k] + kGran - 1) & ~(kGran - 1);
+            }
+            ngran[k] = n[k] / kGran;
+            need[k] = part < nparts && ngran[k] > (own.wend[k] - own.wpos[k]) / kGran; // at most ONE new chunk per flush (csize >= RING)
+        }
+        // hand out chunks (rare: once per chunk per part); warp-uniform bookkeeping, ids in lane order
+        unsigned newid[PPL];
+#pragma unroll
+        for (int k = 0; k < PPL; k++) {
+            newid[k] = kNone;
+            const unsigned m = __ballot_sync(0xffffffffu, need[k]);
+            if (m) {
+                const unsigned sn = __shfl_sync(0xffffffffu, sn_pref, 0);
+                const unsigned i = __popc(m & ((1u << lane) - 1u)), tot = __popc(m), avail = sc_end - sc_next;
+                if (need[k])
+                    newid[k] = i < avail ? sc_next + i : sn + (i - avail);
+                if (tot >= avail) { // the current reservation is used up: switch to the prefetched one, prefetch another
+                    sc_next = sn + (tot - avail);
+                    sc_end = sn + kSuper;
+                    if (lane == 0)
+                        sn_pref = atomicAdd(p.ctl, kSuper);
+                } else {
+                    sc_next += tot;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PPL; k++) {
+            const int part = lane + 32 * k;
+            if (part < nparts && (ngran[k] || final)) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(ring + part * RSTRIDE);
+                for (unsigned g = 0; g < ngran[k]; g++) {
+                    if (own.wpos[k] == own.wend[k]) { // open the next chunk of this list
+                        const unsigned id = newid[k];
+                        if (id >= p.nchunks_cap) { // cannot happen (pool sized for the worst case); stay exact anyway
+                            const unsigned short *e = reinterpret_cast<const unsigned short *>(src + 2 * g);
+                            for (int j = 0; j < kGran; j++)
+                                if (e[j] < p.tile_cells)
+                                    atomicAdd(p.grid + (unsigned long long)part * p.tile_cells + e[j], 1ull);
+                            continue;
+                        }
+                        if (own.cur[k] == kNone)
+                            p.head[(unsigned long long)wglobal * p.nparts_pad + part] = id;
+                        else
+                            p.next[own.cur[k]] = id;
+                        own.cur[k] = id;
+                        own.wpos[k] = id << cshift;
+                        own.wend[k] = own.wpos[k] + csize;
+                    }
+                    const uint4 a = src[2 * g], b = src[2 * g + 1];
+                    uint4 *d = reinterpret_cast<uint4 *>(p.pool + own.wpos[k]);
+                    d[0] = a;
+                    d[1] = b;
+                    own.wpos[k] += kGran;
+                    own.total[k] += kGran;
+                }
+                const unsigned done = ngran[k] * kGran;
+                if (done && n[k] > done) { // move the < 16 leftover entries to the front (source and destination never overlap)
+                    uint4 *dstq = reinterpret_cast<uint4 *>(ring + part * RSTRIDE);
+                    const uint4 a = src[2 * ngran[k]], b = src[2 * ngran[k] + 1];
+                    dstq[0] = a;
+                    dstq[1] = b;
+                }
+                cnt[part] = n[k] - done;
+            }
+        }
+    };
+
+    int st = 0;
+    unsigned phase0 = 0, phase1 = 0;
+    if (lane == 0 && wglobal < nfull)
+        issue(wglobal, 0);
+    for (long long tile = wglobal; tile < ntiles; tile += wtotal) {
+        const long long tbase = p.row0 + tile * TILE;
+        const bool full = tile < nfull;
+        if (full) {
+            if (lane == 0 && tile + wtotal < nfull)
+                issue(tile + wtotal, st ^ 1); // prefetch the next tile while this one is processed
+            mbar_wait(&bars[warp][st], st ? phase1 : phase0);
+            if (st)
+                phase1 ^= 1;
+            else
+                phase0 ^= 1;
+        }
+        const T *buf = cols + st * ND * TILE;
+        const long long tend = min(p.row0 + p.nrows, tbase + TILE);
+#pragma unroll 1
+        for (int grp = 0; grp < FG; grp++) {
+            if (!full && tbase + grp * kGroupRows >= tend)
+                break;
+            unsigned idx[8];
+            unsigned ovf = 0; // bit r: row r of this lane found its ring full
+            if (full)
+                group_rows<T, ND, RING, RSTRIDE, true>(p, buf + grp * kGroupRows, TILE, 0, 0, lane, cnt, ring, idx, ovf);
+            else
+                group_rows<T, ND, RING, RSTRIDE, false>(p, nullptr, 0, tbase + grp * kGroupRows, tend, lane, cnt, ring, idx, ovf);
+            __syncwarp();
+            flush(false);
+            if (__any_sync(0xffffffffu, ovf != 0)) { // a ring filled up inside this group: the excess rows go straight to the grid
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    if (ovf & (1u << r))
+                        atomicAdd(p.grid + idx[r], 1ull);
+            }
+            __syncwarp();
+        }
+        if (full) {
+            fence_proxy_async(); // our generic-proxy reads of this stage are done before the copy engine refills it
+            st ^= 1;
+        }
+    }
+    // ---- the incomplete last granules, then the list descriptors ------------------------------------------------------------
+    flush(true);
+#pragma unroll
+    for (int k = 0; k < PPL; k++) {
+        const int part = lane + 32 * k;
+        if (part < nparts) {
+            if (own.cur[k] != kNone)
+                p.unused[own.cur[k]] = (unsigned short)(own.wend[k] - own.wpos[k]);
+            p.len[(unsigned long long)wglobal * p.nparts_pad + part] = own.total[k];
+        }
+    }
+}
+
+// ---- K2 -------------------------------------------------------------------------------------------------------------------
+// The lists are laid out in the order (part, warp); CTA b takes the b-th of gridDim.x equal shares of that sequence measured in
+// entries, assuming the entries of a part are spread evenly over its warps (they are: the warps take row tiles round-robin).
+__global__ void __launch_bounds__(kCountThreads, 1) k_ring_count(const __grid_constant__ RingParams p) {
+    extern __shared__ __align__(16) unsigned hist[];
+    __shared__ unsigned long long s_part_entries[kMaxParts + 1]; // exclusive prefix over parts
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nparts = p.nparts, npad = p.nparts_pad;
+    const unsigned W = p.nlists_w;
+    // entries per part = sum over warps of len[w][part]
+    for (int part = warp; part < nparts; part += kCountThreads / 32) {
+        unsigned long long s = 0;
+        for (unsigned w = lane; w < W; w += 32)
+            s += p.len[(unsigned long long)w * npad + part];
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0)
+            s_part_entries[part + 1] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        s_part_entries[0] = 0;
+        for (int i = 0; i < nparts; i++)
+            s_part_entries[i + 1] += s_part_entries[i];
+    }
+    __syncthreads();
+    const unsigned long long total = s_part_entries[nparts];
+    const unsigned long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
+    if (lo >= hi)
+        return;
+    const unsigned tc = p.tile_cells;
+    const unsigned cshift = p.chunk_shift, csize = 1u << cshift;
+    for (int part = 0; part < nparts; part++) {
+        const unsigned long long b = s_part_entries[part], e = s_part_entries[part + 1];
+        if (e <= lo || b >= hi || e == b)
+            continue;
+        // the warps [w0, w1) of this part whose lists fall into [lo, hi): boundaries computed identically by both neighbours
+        const unsigned long long n = e - b;
+        const unsigned w0 = lo <= b ? 0u : (unsigned)(((lo - b) * W) / n);
+        const unsigned w1 = hi >= e ? W : (unsigned)(((hi - b) * W) / n);
+        if (w0 >= w1)
+            continue;
+        for (int i = tid; i < (int)(tc / 4 + 1); i += kCountThreads)
+            reinterpret_cast<uint4 *>(hist)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        for (unsigned w = w0 + warp; w < w1; w += kCountThreads / 32) {
+            unsigned id = p.head[(unsigned long long)w * npad + part];
+            while (id != kNone) {
+                const unsigned nx = p.next[id];
+                const unsigned valid = csize - p.unused[id];
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.pool + ((unsigned long long)id << cshift));
+                // a chunk = csize/512 steps of 32 lanes x 16 entries; all loads of a chunk are issued before the first atomic
+                uint4 v[8];
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    const unsigned off = s * 512 + lane * kGran;
+                    if (off < valid) {
+                        v[2 * s] = __ldcs(src + (off >> 3));
+                        v[2 * s + 1] = __ldcs(src + (off >> 3) + 1);
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    const unsigned off = s * 512 + lane * kGran;
+                    if (off < valid) {
+                        const unsigned wd[8] = {v[2 * s].x, v[2 * s].y, v[2 * s].z, v[2 * s].w, v[2 * s + 1].x, v[2 * s + 1].y, v[2 * s + 1].z, v[2 * s + 1].w};
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            atomicAdd(hist + (wd[k] & 0xffffu), 1u); // pads carry tile_cells: the spare cell, never flushed
+                            atomicAdd(hist + (wd[k] >> 16), 1u);
+                        }
+                    }
+                }
+                id = nx;
+            }
+        }
+        __syncthreads();
+        const unsigned long long cell0 = (unsigned long long)part * tc;
+        for (int i = tid; i < (int)tc; i += kCountThreads) {
+            const unsigned c = hist[i];
+            if (c && cell0 + i < p.cells)
+                atomicAdd(p.grid + cell0 + i, (unsigned long long)c);
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, int ND, int PPL, int FG>
+int launch_partition_cfg(int sm_count, cudaStream_t st, RingParams &p, int *warps_out, bool dry) {
+    using L = RingLayout<T, ND, PPL, FG>;
+    constexpr int fit = (int)((113 * 1024 - 512) / L::kPerWarp); // two CTAs per SM
+    constexpr int WARPS = fit > 16 ? 16 : fit;
+    if constexpr (WARPS >= 2) {
+        const long long ntiles = (p.nrows + L::kTileRows - 1) / L::kTileRows;
+        // at least ~8 tiles per warp so that the per-(warp, part) partial chunks stay a small share of the scratch
+        long long blocks = std::min<long long>((ntiles / 8 + WARPS - 1) / WARPS, (long long)sm_count * 2);
+        if (blocks < 1)
+            blocks = 1;
+        *warps_out = (int)blocks * WARPS;
+        if (dry)
+            return B200_OK;
+        auto kern = k_ring_partition<T, ND, PPL, FG, WARPS>;
+        constexpr size_t dyn = L::kPerWarp * WARPS;
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        kern<<<(int)blocks, WARPS * 32, dyn, st>>>(p);
+        B200_CUDA(cudaGetLastError());
+        return B200_OK;
+    } else {
+        *warps_out = 0;
+        return B200_OK;
+    }
+}
+
+template <typename T, int ND>
+int launch_partition_nd(int sm_count, cudaStream_t st, RingParams &p, int fg, int *warps_out, bool dry) {
+    const int ppl = p.nparts_pad / 32;
+    if (ppl == 1)
+        return fg == 2 ? launch_partition_cfg<T, ND, 1, 2>(sm_count, st, p, warps_out, dry) : launch_partition_cfg<T, ND, 1, 1>(sm_count, st, p, warps_out, dry);
+    if (ppl == 2)
+        return launch_partition_cfg<T, ND, 2, 1>(sm_count, st, p, warps_out, dry);
+    return launch_partition_cfg<T, ND, 4, 1>(sm_count, st, p, warps_out, dry);
+}
+
+template <typename T>
+int launch_partition(int nd, int sm_count, cudaStream_t st, RingParams &p, int fg, int *warps_out, bool dry) {
+    switch (nd) {
+    case 1: return launch_partition_nd<T, 1>(sm_count, st, p, fg, warps_out, dry);
+    case 2: return launch_partition_nd<T, 2>(sm_count, st, p, fg, warps_out, dry);
+    default: return launch_partition_nd<T, 3>(sm_count, st, p, fg, warps_out, dry);
+    }
+}
+
+// part == __umulhi(idx, magic) for all idx < cells?  Both sides are monotone step functions of idx, so it suffices to check the
+// last index of every part and the first index of the next one.
+bool magic_exact(unsigned cells, unsigned tile_cells, unsigned magic) {
+    for (unsigned long long k = 0; k * tile_cells < cells; k++) {
+        const unsigned long long first = k * tile_cells, last = std::min<unsigned long long>(first + tile_cells, cells) - 1;
+        if ((unsigned)((first * magic) >> 32) != k || (unsigned)((last * magic) >> 32) != k)
+            return false;
+    }
+    return true;
+}
+
+} // namespace
+
+// Scratch (pool + list tables) lives in the slot; grown on demand.
+int try_launch_ringcount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool vec, bool *taken) {
+    *taken = false;
+    static const bool disabled = getenv("B200_DISABLE_TILECOUNT") && atoi(getenv("B200_DISABLE_TILECOUNT")) != 0;
+    static const int fg = getenv("B200_RING_FG") ? atoi(getenv("B200_RING_FG")) : 1;
+    if (disabled || !vec || bp.nb < 1 || bp.nb > 3 || bp.na != 1 || bp.nrows < (1ll << 22))
+        return B200_OK;
+    const DevAgg &a = bp.a[0];
+    if (a.op != B200_AGG_COUNT || a.data || a.mask)
+        return B200_OK;
+    const unsigned long long cells = bp.cells;
+    if (cells * 4 <= 96 * 1024 || cells > (unsigned long long)kMaxTileCells * kMaxParts || cells >= (1ull << 22))
+        return B200_OK; // small grids: shared-memory privatisation; huge grids: direct REDs / region sort
+    const int t = bp.b[0].dtype;
+    if (t != B200_F32 && t != B200_F64)
+        return B200_OK;
+    RingParams p;
+    memset(&p, 0, sizeof p);
+    for (int i = 0; i < bp.nb; i++) {
+        const DevBinner &b = bp.b[i];
+        if (b.kind != B200_BINNER_SCALAR || b.dtype != t || b.byteswap || b.mask || b.bins < 1 || b.bins >= (1ull << 30))
+            return B200_OK;
+        p.x[i] = b.data;
+        p.vmin[i] = b.vmin;
+        p.scale[i] = b.scale;
+        p.bins_d[i] = b.bins_d;
+        p.bins[i] = (unsigned)b.bins;
+        p.stride[i] = (unsigned)b.stride;
+        p.stride_sum += (unsigned)b.stride;
+    }
+    // as few parts as possible (32, else 64, else 128): the ring memory of k_ring_partition scales with the parts per lane;
+    // tile_cells is nudged upwards until the one-instruction division is exact
+    unsigned tile_cells = 0, magic = 0;
+    for (int np = 32; np <= kMaxParts && !tile_cells; np *= 2) {
+        unsigned long long tcells = ((cells + np - 1) / np + 7) / 8 * 8;
+        for (int tries = 0; tries < 64 && tcells <= kMaxTileCells; tries++, tcells += 8) {
+            const unsigned m = (unsigned)((1ull << 32) / tcells) + 1u;
+            if (magic_exact((unsigned)cells, (unsigned)tcells, m)) {
+                tile_cells = (unsigned)tcells;
+                magic = m;
+                break;
+            }
+        }
+    }
+    if (!tile_cells)
+        return B200_OK;
+    p.cells = (unsigned)cells;
+    p.tile_cells = tile_cells;
+    p.magic = magic;
+    p.nparts = (int)((cells + tile_cells - 1) / tile_cells);
+    p.nparts_pad = p.nparts <= 32 ? 32 : p.nparts <= 64 ? 64 : 128;
+    p.grid = static_cast<unsigned long long *>(a.grid);
+
+    const long long batch = std::min<long long>(bp.nrows, 1ll << 30);
+    p.row0 = 0;
+    p.nrows = batch;
+    int nwarps = 0;
+    if (t == B200_F32)
+        B200_CHECK(launch_partition<float>(bp.nb, ctx->sm_count, nullptr, p, fg, &nwarps, true));
+    else
+        B200_CHECK(launch_partition<double>(bp.nb, ctx->sm_count, nullptr, p, fg, &nwarps, true));
+    if (nwarps <= 0)
+        return B200_OK;
+    // chunk size: about a quarter of a (warp, part) list, within 512..2048 entries
+    unsigned cshift = 9;
+    while (cshift < 11 && (unsigned long long)batch / ((unsigned long long)nwarps * p.nparts) >= (8ull << cshift))
+        cshift++;
+    p.chunk_shift = cshift;
+    p.nlists_w = (unsigned)nwarps;
+    // every list wastes less than one chunk, every warp less than one reservation (+ its prefetched one)
+    const unsigned long long nchunks = ((unsigned long long)batch >> cshift) + (unsigned long long)nwarps * (p.nparts + 2 * kSuper) + 2 * kSuper;
+    if ((nchunks << cshift) >= (1ull << 32))
+        return B200_OK;
+    p.nchunks_cap = (unsigned)nchunks;
+    const size_t lists = (size_t)nwarps * p.nparts_pad;
+    // layout: [ctl 256 B | len | unused] (zeroed)  [head | next] (0xFF)  [pool]
+    const size_t off_len = 256, off_unused = align_up(off_len + lists * 4, 256), zero_end = align_up(off_unused + nchunks * 2, 256);
+    const size_t off_head = zero_end, off_next = align_up(off_head + lists * 4, 256), ff_end = align_up(off_next + nchunks * 4, 256);
+    const size_t off_pool = ff_end, need = off_pool + (nchunks << cshift) * 2;
+    if (slot->scratch_cap < need) {
+        if (slot->scratch) {
+            B200_CUDA(cudaStreamSynchronize(slot->stream));
+            B200_CUDA(cudaFree(slot->scratch));
+            slot->scratch = nullptr;
+            slot->scratch_cap = 0;
+        }
+        cudaError_t e = cudaMalloc(&slot->scratch, need);
+        if (e != cudaSuccess) { // not enough memory for the pool: the direct RED kernel takes the call
+            cudaGetLastError();
+            return B200_OK;
+        }
+        slot->scratch_cap = need;
+    }
+    char *base = static_cast<char *>(slot->scratch);
+    p.ctl = reinterpret_cast<unsigned *>(base);
+    p.len = reinterpret_cast<unsigned *>(base + off_len);
+    p.unused = reinterpret_cast<unsigned short *>(base + off_unused);
+    p.head = reinterpret_cast<unsigned *>(base + off_head);
+    p.next = reinterpret_cast<unsigned *>(base + off_next);
+    p.pool = reinterpret_cast<unsigned short *>(base + off_pool);
+    cudaStream_t st = slot->stream;
+    B200_CUDA(cudaFuncSetAttribute(k_ring_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kMaxTileCells + 1) * 4)));
+    const size_t hist_bytes = ((size_t)tile_cells / 4 + 1) * 16;
+    for (long long r0 = 0; r0 < bp.nrows; r0 += batch) {
+        p.row0 = r0;
+        p.nrows = std::min<long long>(batch, bp.nrows - r0);
+        B200_CUDA(cudaMemsetAsync(base, 0, zero_end, st));
+        B200_CUDA(cudaMemsetAsync(base + off_head, 0xFF, ff_end - off_head, st));
+        int w = 0;
+        if (t == B200_F32)
+            B200_CHECK(launch_partition<float>(bp.nb, ctx->sm_count, st, p, fg, &w, false));
+        else
+            B200_CHECK(launch_partition<double>(bp.nb, ctx->sm_count, st, p, fg, &w, false));
+        p.nlists_w = (unsigned)w; // the last batch may launch fewer warps; its lists are the first w rows of head[] / len[]
+        k_ring_count<<<ctx->sm_count, kCountThreads, hist_bytes, st>>>(p);
+        B200_CUDA(cudaGetLastError());
+    }
+    *taken = true;
+    return B200_OK;
+}
+
+} // namespace b200

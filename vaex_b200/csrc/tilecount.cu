@@ -53,13 +53,6 @@ constexpr unsigned kNone = 0xFFFFFFFFu, kOver = 0xFFFFFFFEu;
 constexpr unsigned long long kNone64 = ~0ull;
 constexpr unsigned short kPad = 0xFFFFu; // padding entry (>= 32768: not a cell)
 
-__device__ __forceinline__ unsigned bin_index(double v, double vmin, double scale, double bins_d, unsigned bins) {
-    // identical to fast.cu: one saturating round-down conversion + clamp, NaN tested on `scaled` (src/binners.cpp:13-57)
-    const double scaled = __dmul_rn(__dsub_rn(v, vmin), scale);
-    const int i = __double2int_rd(__dmul_rn(scaled, bins_d));
-    const unsigned idx = (unsigned)(min(max(i, -1), (int)bins) + 2);
-    return scaled != scaled ? 0u : idx;
-}
 
 template <typename T>
 __device__ __forceinline__ void load4(const void *p, long long i, double out[4]);

@@ -45,13 +45,6 @@ constexpr unsigned kPadIdx = 0xFFFFFFFFu;
 constexpr int kSlice = 2048;            // bucket entries per k_sort_apply CTA: small, so that the CTAs resident at any moment
                                         // (148 x 8) span only a few regions and their cells stay in the L2
 
-__device__ __forceinline__ unsigned bin_index(double v, double vmin, double scale, double bins_d, unsigned bins) {
-    // identical to fast.cu (src/binners.cpp:13-57)
-    const double scaled = __dmul_rn(__dsub_rn(v, vmin), scale);
-    const int i = __double2int_rd(__dmul_rn(scaled, bins_d));
-    const unsigned idx = (unsigned)(min(max(i, -1), (int)bins) + 2);
-    return scaled != scaled ? 0u : idx;
-}
 
 template <typename T>
 __device__ __forceinline__ void load4(const void *p, long long i, double out[4]);
