@@ -124,6 +124,12 @@ int b200_ctx_sync(b200_ctx *ctx, int slot /* -1 = all */);
 int b200_ctx_device(const b200_ctx *ctx);
 /* raw cudaStream_t of a slot, so host code can order its own work (NCCL, timing events) after ours */
 int b200_ctx_stream(b200_ctx *ctx, int slot, void **stream_out);
+/* Counters of the last partitioned count(*) batch on this slot (csrc/ringcount.cu), read back from the device after a stream
+ * sync — bench.py derives the scratch traffic of the timed build from them instead of quoting a profiler constant:
+ * out[0] rows of the batch, out[1] 16-bit entries written to (and read back from) the scratch pool, pads included,
+ * out[2] chunks reserved, out[3] entries per chunk, out[4] bytes memset before the batch, out[5] (warp, part) lists.
+ * All zero when the slot has not run that path.  No reference counterpart (instrumentation). */
+int b200_ctx_path_stats(b200_ctx *ctx, int slot, uint64_t out[6]);
 
 /* ---- aggregators --------------------------------------------------------------------------- */
 int b200_agg_create(b200_ctx *ctx, int op, int dtype, int dtype2, int byteswap, uint32_t moment, uint64_t cells, b200_agg **out);

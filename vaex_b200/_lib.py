@@ -95,6 +95,7 @@ def lib():
             "b200_ctx_sync": (i32, [vp, i32]),
             "b200_ctx_device": (i32, [vp]),
             "b200_ctx_stream": (i32, [vp, i32, P(vp)]),
+            "b200_ctx_path_stats": (i32, [vp, i32, P(u64)]),
             "b200_agg_create": (i32, [vp, i32, i32, i32, i32, u32, u64, P(vp)]),
             "b200_agg_destroy": (i32, [vp]),
             "b200_agg_reset": (i32, [vp]),
@@ -174,6 +175,12 @@ class Context:
 
     def sync(self, slot=-1):
         check(lib().b200_ctx_sync(self._h, int(slot)))
+
+    def path_stats(self, slot=0):
+        """Counters of the last partitioned count(*) batch on this slot (include/b200agg.h b200_ctx_path_stats)."""
+        out = (C.c_uint64 * 6)()
+        check(lib().b200_ctx_path_stats(self._h, int(slot), out))
+        return dict(rows=out[0], entries=out[1], chunks=out[2], chunk_entries=out[3], memset_bytes=out[4], lists=out[5])
 
     def stream(self, slot=0):
         s = C.c_void_p()

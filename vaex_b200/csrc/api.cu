@@ -297,6 +297,30 @@ int b200_ctx_stream(b200_ctx *ctx, int slot, void **stream_out) {
     return B200_OK;
 }
 
+int b200_ctx_path_stats(b200_ctx *ctx, int slot, uint64_t out[6]) {
+    if (!ctx || slot < 0 || slot >= ctx->nslots || !out) {
+        set_error("b200_ctx_path_stats: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    Slot *s = ctx->slots[slot];
+    memset(out, 0, 6 * sizeof(uint64_t));
+    B200_CUDA(cudaSetDevice(ctx->device));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    const char *lo = static_cast<const char *>(s->scratch), *hi = lo + s->scratch_cap;
+    const char *q = reinterpret_cast<const char *>(s->ring_len);
+    if (!q || q < lo || q + s->ring_lists * 4 > hi) // never ran, or the scratch was reallocated since
+        return B200_OK;
+    std::vector<unsigned> len(s->ring_lists);
+    unsigned chunks = 0;
+    B200_CUDA(cudaMemcpy(len.data(), s->ring_len, s->ring_lists * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(&chunks, s->ring_ctl, 4, cudaMemcpyDeviceToHost));
+    uint64_t entries = 0;
+    for (unsigned v : len)
+        entries += v;
+    out[0] = s->ring_rows, out[1] = entries, out[2] = chunks, out[3] = s->ring_chunk_entries, out[4] = s->ring_memset_bytes, out[5] = s->ring_lists;
+    return B200_OK;
+}
+
 // ---- aggregators -----------------------------------------------------------------------------------
 int b200_agg_create(b200_ctx *ctx, int op, int dtype, int dtype2, int byteswap, uint32_t moment, uint64_t cells, b200_agg **out) {
     if (!ctx || !out || op < B200_AGG_COUNT || op > B200_AGG_NUNIQUE || dtype < 0 || dtype >= B200_NDTYPE || dtype2 < 0 || dtype2 >= B200_NDTYPE) {

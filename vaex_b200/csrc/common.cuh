@@ -75,8 +75,12 @@ struct Slot {
     size_t stage_cap = 0;
     void *pinned = nullptr; // small pinned scratch (results of reductions)
     void *dscratch = nullptr;
-    void *scratch = nullptr; // tilecount buckets
+    void *scratch = nullptr; // partition scratch (ringcount pool + list tables, tilesort buckets)
     size_t scratch_cap = 0;
+    // the last ringcount batch on this slot, for b200_ctx_path_stats (device pointers into `scratch`)
+    const unsigned *ring_len = nullptr, *ring_ctl = nullptr;
+    size_t ring_lists = 0;
+    uint64_t ring_rows = 0, ring_memset_bytes = 0, ring_chunk_entries = 0;
     std::mutex mu;
 };
 

@@ -3,16 +3,18 @@
 // Why two kernels: a direct kernel issues one RED per row, and the L2 retires only ~98 sector operations per clock chip-wide,
 // loads included (profiles/r01_ncu_fast.txt), which caps the 2-D 1024^2 count at ~1.5e11 rows/s = 18 % of the HBM stream rate.
 // Shared-memory atomics retire ~6 lanes/clk/SM, 9x more, but a 1027^2 grid is 4 MB even with 32-bit counters.  So the grid is
-// cut into <= 32 (else 64 / 128) GRID TILES ("parts") of <= 49152 consecutive cells and the rows are partitioned by part first:
+// cut into <= 32 (else 64) GRID TILES ("parts") of <= 49152 consecutive cells and the rows are partitioned by part first:
 //
 //   K1 k_ring_partition  every WARP is autonomous.  Columns are staged by TMA (cp.async.bulk + mbarrier, double buffered).
 //                        Per row: the bit-exact fp64 bin index, part = idx / tile_cells (one IMAD.HI), ONE shared-memory atomic
-//                        on the (warp, part) counter whose return value is the row's slot in that part's RING, and one 16-bit
-//                        store of the local cell index into the ring.  Every 256 rows each lane — lane l OWNS part l — flushes
-//                        the complete 16-entry granules (one 32-byte sector each: two LDS.128 + two STG.128) of its ring to the
-//                        part's current CHUNK in global memory and moves the < 16 leftover entries to the ring's front.
+//                        on the (warp, part) counter whose return value is the row's slot in that part's RING (96 entries), and
+//                        one 16-bit store of the local cell index into the ring.  Every 256 rows the rings that hold a full
+//                        LINE (64 entries = 128 bytes) append it to the part's current CHUNK in global memory — half a warp per
+//                        line: one LDS.64 + one coalesced STG.64 per lane — and slide the <= 32 entries behind it to the front.
 //                        There is no scan, no scatter pass and no copy-out pass: round 1's kernel spent 47 of its 77 warp
-//                        instructions per 32 rows there (profiles/r01_ncu_final_k1_phases.txt).
+//                        instructions per 32 rows there (profiles/r01_ncu_final_k1_phases.txt).  (A first version flushed
+//                        16-entry granules from the owner lanes: 7.5 of its 16.9 shared-memory/L1 wavefronts per 32 rows went
+//                        into those divergent 16-byte accesses, profiles/r02_ncu_ring_v1.txt.)
 //                        Chunks (512..2048 entries) come from ONE pool: a warp reserves 32 chunks with one global atomic and
 //                        hands them to its parts with a ballot; the chunks of a (warp, part) form a linked list (next[]), its
 //                        head and entry count go to head[] / len[].  No per-part bucket provisioning, no overflow fallback, and
@@ -23,7 +25,8 @@
 //                        RED.ADD.64 each when the part changes (1-2 flushes per CTA).
 //
 // HBM traffic: 8 B/row of columns + 2 B/row written + 2 B/row read.  Exact integer counts, same grid layout, any distribution:
-// a ring that fills up inside one 256-row group (> 48 rows of a warp in one part) sends the excess rows to direct REDs.
+// a ring that fills up inside one 256-row group (> 32 rows of a warp in one part on top of a full leftover) sends the excess rows
+// to direct REDs.
 #include <algorithm>
 
 #include "binby.cuh"
@@ -40,6 +43,7 @@ struct RingParams {
     long long row0, nrows;        // this batch
     unsigned cells;
     unsigned tile_cells;          // cells per part (<= 49151): part = idx / tile_cells, local = idx % tile_cells < 2^16
+    unsigned neg_tile_cells;      // 2^32 - tile_cells: local = idx + part * neg_tile_cells in one IMAD
     unsigned magic;               // part == __umulhi(idx, magic) for every idx < cells (verified on the host)
     int nparts;
     int nparts_pad;               // 32 * PPL
@@ -58,10 +62,11 @@ struct RingParams {
 namespace {
 
 constexpr int kGroupRows = 256;   // rows between two ring flushes: 8 per lane
-constexpr int kGran = 16;         // entries per flush granule = one 32-byte sector
+constexpr int kGran = 16;         // entries per lane and step in k_ring_count
+constexpr unsigned kLine = 64;    // entries a ring flush moves = one 128-byte line
 constexpr unsigned kSuper = 32;   // chunks a warp reserves from the pool at a time
 constexpr unsigned kMaxTileCells = 49151; // 192 KB of u32 counters in k_ring_count, one of them the pad cell
-constexpr int kMaxParts = 128;
+constexpr int kMaxParts = 64;
 constexpr unsigned kNone = 0xFFFFFFFFu;
 constexpr int kCountThreads = 1024;
 
@@ -122,9 +127,12 @@ __device__ __forceinline__ void ldg4<double>(const void *p, long long i, double 
 
 // one group of 256 rows (8 per lane): bit-exact index, part, ONE shared-memory atomic for the slot, one 16-bit store.
 // STAGED: the columns sit in shared memory (TMA), every row exists.  Otherwise: global loads with bounds (the ragged last tile).
+// Returns the largest slot a row of this lane was given (>= RING: that row did not fit, see `overflow`); slots[] = kNone marks
+// rows that do not exist.
 template <typename T, int ND, int RING, int RSTRIDE, bool STAGED>
-__device__ __forceinline__ void group_rows(const RingParams &p, const T *buf, int col_stride, long long gbase, long long tend, int lane, unsigned *cnt,
-                                           unsigned short *ring, unsigned idx[8], unsigned &ovf) {
+__device__ __forceinline__ unsigned group_rows(const RingParams &p, const T *buf, int col_stride, long long gbase, long long tend, int lane, unsigned *cnt,
+                                               unsigned short *ring, unsigned idx[8], unsigned slots[8]) {
+    unsigned worst = 0;
 #pragma unroll
     for (int q = 0; q < 2; q++) {
         double c[ND][4];
@@ -151,27 +159,30 @@ __device__ __forceinline__ void group_rows(const RingParams &p, const T *buf, in
             for (int d = 0; d < ND; d++)
                 id += (unsigned)bin_cell_m1(c[d][j], p.vmin[d], p.scale[d], p.bins_d[d], p.bins[d]) * p.stride[d];
             idx[q * 4 + j] = id;
+            slots[q * 4 + j] = kNone;
             if (STAGED || gbase + r0 + j < tend) {
                 const unsigned part = __umulhi(id, p.magic);
                 const unsigned slot = atomicAdd(cnt + part, 1u);
+                slots[q * 4 + j] = slot;
+                worst = max(worst, slot);
                 if (slot < (unsigned)RING)
-                    ring[part * RSTRIDE + slot] = (unsigned short)(id - part * p.tile_cells);
-                else
-                    ovf |= 1u << (q * 4 + j);
+                    ring[part * RSTRIDE + slot] = (unsigned short)(id + part * p.neg_tile_cells);
             }
         }
     }
+    return worst;
 }
 
-// shared memory of one warp: [2 stages x ND columns x TILE rows of T] [rings: 32*PPL parts x RING u16] [counters: 32*PPL u32]
+// shared memory of one warp: [2 stages x ND columns x TILE rows of T] [rings: 32*PPL parts x (RING + 8) u16] [counters: 32*PPL u32]
+// A ring holds < 64 entries left over from the last flush + the new ones of one group; a flush moves whole LINES of 64 entries
+// (128 bytes).  With <= 32 new entries per part and group the ring never fills (the busiest part of the headline workload takes
+// 19 +- 4 of a group's 256 rows); rows that find it full go to direct REDs.
 template <typename T, int ND, int PPL, int FG>
 struct RingLayout {
     static constexpr int kTileRows = kGroupRows * FG;
-    static constexpr int kRing = PPL <= 2 ? 64 : 32; // ring entries per part: < 16 left over + up to RING-15 new ones per group
+    static constexpr int kRing = 96;
+    static constexpr int kRingStride = kRing + 8; // 208 bytes: 16-byte aligned rows that rotate over the banks
     static constexpr size_t kColBytes = 2ull * ND * kTileRows * sizeof(T);
-    // rows of RING + 8 entries: the 16-byte pad rotates consecutive parts over the banks, so the owners' LDS.128 / STS.128 of a
-    // flush (lane l -> row l) do not all hit banks 0-3
-    static constexpr int kRingStride = kRing + 8;
     static constexpr size_t kRingBytes = 32ull * PPL * kRingStride * 2;
     static constexpr size_t kCntBytes = 32ull * PPL * 4;
     static constexpr size_t kPerWarp = kColBytes + kRingBytes + kCntBytes;
@@ -190,6 +201,7 @@ template <typename T, int ND, int PPL, int FG, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 2) k_ring_partition(const __grid_constant__ RingParams p) {
     using L = RingLayout<T, ND, PPL, FG>;
     constexpr int RING = L::kRing, RSTRIDE = L::kRingStride;
+    static_assert(RING - kLine <= 32 && (RSTRIDE * 2) % 16 == 0, "ring geometry");
     constexpr int TILE = L::kTileRows;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ __align__(8) unsigned long long bars[WARPS][2];
@@ -209,10 +221,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_ring_partition(const __grid_c
         cnt[lane + 32 * k] = 0;
     __syncwarp();
 
-    const int nparts = p.nparts;
     const unsigned cshift = p.chunk_shift, csize = 1u << cshift;
-    const long long ntiles = (p.nrows + TILE - 1) / TILE;
-    const long long nfull = p.nrows / TILE; // tiles [0, nfull) are complete (and TMA staged)
+    const long long nfull = p.nrows / TILE; // tiles [0, nfull) are complete and TMA staged; the ragged rest is one more tile
     const long long wglobal = (long long)blockIdx.x * WARPS + warp, wtotal = (long long)gridDim.x * WARPS;
 
     Owner<PPL> own;
@@ -224,41 +234,31 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_ring_partition(const __grid_c
     if (lane == 0)
         sn_pref = atomicAdd(p.ctl, kSuper);
 
-    auto issue = [&](long long t, int st) { // lane 0: start the bulk copies of tile t's columns into stage st
-        mbar_expect_tx(&bars[warp][st], (unsigned)(ND * TILE * sizeof(T)));
-#pragma unroll
-        for (int d = 0; d < ND; d++)
-            tma_load_1d(cols + (st * ND + d) * TILE, static_cast<const T *>(p.x[d]) + p.row0 + t * TILE, (unsigned)(TILE * sizeof(T)), &bars[warp][st]);
-    };
-
-    // ---- flush: every lane appends the complete granules of the rings it owns to their chunk lists -----------------------------
-    // `final`: also the incomplete last granule, padded with entries == tile_cells (the pad cell of k_ring_count)
+    // ---- flush: every ring that holds a full LINE (64 entries = 128 bytes) appends it to its chunk list -------------------------
+    // The owners (lane l owns parts l, l+32) do the bookkeeping in parallel: chunk switch, write position, counter.  Then the warp
+    // moves the lines, FOUR parts per step: a quarter-warp copies one line with one LDS.128 + one coalesced STG.128 per lane and
+    // slides the <= 32 entries behind it to the ring's front.  `final`: the incomplete last line too, padded with entries ==
+    // tile_cells (k_ring_count's spare cell).
     auto flush = [&](bool final) {
-        unsigned n[PPL], ngran[PPL];
-        bool need[PPL];
 #pragma unroll
         for (int k = 0; k < PPL; k++) {
             const int part = lane + 32 * k;
-            n[k] = min(cnt[part], (unsigned)RING); // rows past RING went to direct REDs (`ovf` below)
-            if (final && (n[k] & (kGran - 1))) {
-                for (unsigned e = n[k]; e < ((n[k] + kGran - 1) & ~(kGran - 1)); e++)
+            unsigned n = min(cnt[part], (unsigned)RING); // rows past RING went to direct REDs
+            if (final && n > 0 && n < kLine) {
+                for (unsigned e = n; e < kLine; e++)
                     ring[part * RSTRIDE + e] = (unsigned short)p.tile_cells;
-                n[k] = (n[k] + kGran - 1) & ~(kGran - 1);
+                n = kLine;
             }
-            ngran[k] = n[k] / kGran;
-            need[k] = part < nparts && ngran[k] > (own.wend[k] - own.wpos[k]) / kGran; // at most ONE new chunk per flush (csize >= RING)
-        }
-        // hand out chunks (rare: once per chunk per part); warp-uniform bookkeeping, ids in lane order
-        unsigned newid[PPL];
-#pragma unroll
-        for (int k = 0; k < PPL; k++) {
-            newid[k] = kNone;
-            const unsigned m = __ballot_sync(0xffffffffu, need[k]);
-            if (m) {
+            const bool has = n >= kLine; // cnt of parts >= nparts stays 0
+            const bool need = has && own.wpos[k] == own.wend[k];
+            // hand out chunks (rare: once per chunk per part); warp-uniform bookkeeping, ids in lane order
+            unsigned newid = kNone;
+            const unsigned mneed = __ballot_sync(0xffffffffu, need);
+            if (mneed) {
                 const unsigned sn = __shfl_sync(0xffffffffu, sn_pref, 0);
-                const unsigned i = __popc(m & ((1u << lane) - 1u)), tot = __popc(m), avail = sc_end - sc_next;
-                if (need[k])
-                    newid[k] = i < avail ? sc_next + i : sn + (i - avail);
+                const unsigned i = __popc(mneed & ((1u << lane) - 1u)), tot = __popc(mneed), avail = sc_end - sc_next;
+                if (need)
+                    newid = i < avail ? sc_next + i : sn + (i - avail);
                 if (tot >= avail) { // the current reservation is used up: switch to the prefetched one, prefetch another
                     sc_next = sn + (tot - avail);
                     sc_end = sn + kSuper;
@@ -268,98 +268,117 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_ring_partition(const __grid_c
                     sc_next += tot;
                 }
             }
-        }
-#pragma unroll
-        for (int k = 0; k < PPL; k++) {
-            const int part = lane + 32 * k;
-            if (part < nparts && (ngran[k] || final)) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(ring + part * RSTRIDE);
-                for (unsigned g = 0; g < ngran[k]; g++) {
-                    if (own.wpos[k] == own.wend[k]) { // open the next chunk of this list
-                        const unsigned id = newid[k];
-                        if (id >= p.nchunks_cap) { // cannot happen (pool sized for the worst case); stay exact anyway
-                            const unsigned short *e = reinterpret_cast<const unsigned short *>(src + 2 * g);
-                            for (int j = 0; j < kGran; j++)
-                                if (e[j] < p.tile_cells)
-                                    atomicAdd(p.grid + (unsigned long long)part * p.tile_cells + e[j], 1ull);
-                            continue;
-                        }
-                        if (own.cur[k] == kNone)
-                            p.head[(unsigned long long)wglobal * p.nparts_pad + part] = id;
-                        else
-                            p.next[own.cur[k]] = id;
-                        own.cur[k] = id;
-                        own.wpos[k] = id << cshift;
-                        own.wend[k] = own.wpos[k] + csize;
+            unsigned wp = kNone; // pool entry index where this part's line goes
+            if (has) {
+                if (need && newid < p.nchunks_cap) { // open the next chunk of this list
+                    if (own.cur[k] == kNone)
+                        p.head[(unsigned long long)wglobal * p.nparts_pad + part] = newid;
+                    else
+                        p.next[own.cur[k]] = newid;
+                    own.cur[k] = newid;
+                    own.wpos[k] = newid << cshift;
+                    own.wend[k] = own.wpos[k] + csize;
+                }
+                if (own.wpos[k] != own.wend[k]) {
+                    wp = own.wpos[k];
+                    own.wpos[k] += kLine;
+                    own.total[k] += kLine;
+                } else { // pool exhausted: cannot happen (sized for the worst case); stay exact anyway
+                    for (unsigned e = 0; e < kLine; e++) {
+                        const unsigned c = ring[part * RSTRIDE + e];
+                        if (c < p.tile_cells)
+                            atomicAdd(p.grid + (unsigned long long)part * p.tile_cells + c, 1ull);
                     }
-                    const uint4 a = src[2 * g], b = src[2 * g + 1];
-                    uint4 *d = reinterpret_cast<uint4 *>(p.pool + own.wpos[k]);
-                    d[0] = a;
-                    d[1] = b;
-                    own.wpos[k] += kGran;
-                    own.total[k] += kGran;
                 }
-                const unsigned done = ngran[k] * kGran;
-                if (done && n[k] > done) { // move the < 16 leftover entries to the front (source and destination never overlap)
-                    uint4 *dstq = reinterpret_cast<uint4 *>(ring + part * RSTRIDE);
-                    const uint4 a = src[2 * ngran[k]], b = src[2 * ngran[k] + 1];
-                    dstq[0] = a;
-                    dstq[1] = b;
+                cnt[part] = n - kLine;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, has);
+            const int quarter = lane >> 3, ql = lane & 7;
+            while (m) {
+                int src = -1;
+#pragma unroll
+                for (int j = 0; j < 4; j++) { // the j-th lowest owner with a line goes to quarter-warp j
+                    const int bit = m ? __ffs(m) - 1 : -1;
+                    if (j == quarter)
+                        src = bit;
+                    m &= m - 1; // 0 stays 0
                 }
-                cnt[part] = n[k] - done;
+                const unsigned wps = __shfl_sync(0xffffffffu, wp, src < 0 ? 0 : src);
+                if (src >= 0) {
+                    uint4 *r = reinterpret_cast<uint4 *>(ring + (src + 32 * k) * RSTRIDE);
+                    const uint4 w = r[ql];
+                    uint4 up = make_uint4(0, 0, 0, 0);
+                    if (ql < (RING - kLine) / 8)
+                        up = r[kLine / 8 + ql];
+                    if (wps != kNone)
+                        reinterpret_cast<uint4 *>(p.pool + wps)[ql] = w;
+                    if (ql < (RING - kLine) / 8)
+                        r[ql] = up; // the entries behind the line slide to the front (each lane rewrites the 16 bytes it read)
+                }
             }
         }
     };
+    // rows that found their ring full (slot >= RING) go straight to the grid; `slots` are the atomics' return values of one group
+    auto overflow = [&](const unsigned idx[8], const unsigned slots[8]) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            if (slots[r] >= (unsigned)RING && slots[r] != kNone)
+                atomicAdd(p.grid + idx[r], 1ull);
+    };
 
-    int st = 0;
-    unsigned phase0 = 0, phase1 = 0;
+    // ---- complete tiles: columns staged by TMA, double buffered ---------------------------------------------------------------
+    const unsigned bar0 = smem_u32(&bars[warp][0]);
+    const unsigned col0 = smem_u32(cols);
+    constexpr unsigned kStageBytes = ND * TILE * sizeof(T), kColTileBytes = TILE * sizeof(T);
+    auto issue = [&](long long t, unsigned st) { // lane 0: start the bulk copies of tile t's columns into stage st
+        const unsigned bar = bar0 + 8 * st;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kStageBytes) : "memory");
+#pragma unroll
+        for (int d = 0; d < ND; d++)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(col0 + st * kStageBytes + d * kColTileBytes),
+                         "l"(static_cast<const T *>(p.x[d]) + p.row0 + t * TILE), "r"(kColTileBytes), "r"(bar)
+                         : "memory");
+    };
+    unsigned it = 0; // tiles this warp has consumed: stage = it & 1, mbarrier parity = (it >> 1) & 1
     if (lane == 0 && wglobal < nfull)
         issue(wglobal, 0);
-    for (long long tile = wglobal; tile < ntiles; tile += wtotal) {
-        const long long tbase = p.row0 + tile * TILE;
-        const bool full = tile < nfull;
-        if (full) {
-            if (lane == 0 && tile + wtotal < nfull)
-                issue(tile + wtotal, st ^ 1); // prefetch the next tile while this one is processed
-            mbar_wait(&bars[warp][st], st ? phase1 : phase0);
-            if (st)
-                phase1 ^= 1;
-            else
-                phase0 ^= 1;
-        }
+    for (long long tile = wglobal; tile < nfull; tile += wtotal, it++) {
+        const unsigned st = it & 1;
+        if (lane == 0 && tile + wtotal < nfull)
+            issue(tile + wtotal, st ^ 1); // prefetch the next tile while this one is processed
+        mbar_wait(&bars[warp][st], (it >> 1) & 1);
         const T *buf = cols + st * ND * TILE;
-        const long long tend = min(p.row0 + p.nrows, tbase + TILE);
 #pragma unroll 1
         for (int grp = 0; grp < FG; grp++) {
-            if (!full && tbase + grp * kGroupRows >= tend)
-                break;
-            unsigned idx[8];
-            unsigned ovf = 0; // bit r: row r of this lane found its ring full
-            if (full)
-                group_rows<T, ND, RING, RSTRIDE, true>(p, buf + grp * kGroupRows, TILE, 0, 0, lane, cnt, ring, idx, ovf);
-            else
-                group_rows<T, ND, RING, RSTRIDE, false>(p, nullptr, 0, tbase + grp * kGroupRows, tend, lane, cnt, ring, idx, ovf);
+            unsigned idx[8], slots[8];
+            const unsigned worst = group_rows<T, ND, RING, RSTRIDE, true>(p, buf + grp * kGroupRows, TILE, 0, 0, lane, cnt, ring, idx, slots);
             __syncwarp();
             flush(false);
-            if (__any_sync(0xffffffffu, ovf != 0)) { // a ring filled up inside this group: the excess rows go straight to the grid
-#pragma unroll
-                for (int r = 0; r < 8; r++)
-                    if (ovf & (1u << r))
-                        atomicAdd(p.grid + idx[r], 1ull);
-            }
+            if (__any_sync(0xffffffffu, worst >= (unsigned)RING))
+                overflow(idx, slots);
             __syncwarp();
         }
-        if (full) {
-            fence_proxy_async(); // our generic-proxy reads of this stage are done before the copy engine refills it
-            st ^= 1;
+        fence_proxy_async(); // our generic-proxy reads of this stage are done before the copy engine refills it
+    }
+    // ---- the ragged last tile (global loads with bounds), taken by the warp whose turn it is -------------------------------------
+    if (nfull * TILE < p.nrows && nfull % wtotal == wglobal) {
+        const long long tbase = p.row0 + nfull * TILE, tend = p.row0 + p.nrows;
+        for (int grp = 0; tbase + grp * kGroupRows < tend; grp++) {
+            unsigned idx[8], slots[8];
+            const unsigned worst = group_rows<T, ND, RING, RSTRIDE, false>(p, nullptr, 0, tbase + grp * kGroupRows, tend, lane, cnt, ring, idx, slots);
+            __syncwarp();
+            flush(false);
+            if (__any_sync(0xffffffffu, worst >= (unsigned)RING))
+                overflow(idx, slots);
+            __syncwarp();
         }
     }
-    // ---- the incomplete last granules, then the list descriptors ------------------------------------------------------------
+    // ---- the incomplete last lines, then the list descriptors ---------------------------------------------------------------
     flush(true);
 #pragma unroll
     for (int k = 0; k < PPL; k++) {
         const int part = lane + 32 * k;
-        if (part < nparts) {
+        if (part < p.nparts) {
             if (own.cur[k] != kNone)
                 p.unused[own.cur[k]] = (unsigned short)(own.wend[k] - own.wpos[k]);
             p.len[(unsigned long long)wglobal * p.nparts_pad + part] = own.total[k];
@@ -486,9 +505,7 @@ int launch_partition_nd(int sm_count, cudaStream_t st, RingParams &p, int fg, in
     const int ppl = p.nparts_pad / 32;
     if (ppl == 1)
         return fg == 2 ? launch_partition_cfg<T, ND, 1, 2>(sm_count, st, p, warps_out, dry) : launch_partition_cfg<T, ND, 1, 1>(sm_count, st, p, warps_out, dry);
-    if (ppl == 2)
-        return launch_partition_cfg<T, ND, 2, 1>(sm_count, st, p, warps_out, dry);
-    return launch_partition_cfg<T, ND, 4, 1>(sm_count, st, p, warps_out, dry);
+    return launch_partition_cfg<T, ND, 2, 1>(sm_count, st, p, warps_out, dry);
 }
 
 template <typename T>
@@ -561,9 +578,10 @@ int try_launch_ringcount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
         return B200_OK;
     p.cells = (unsigned)cells;
     p.tile_cells = tile_cells;
+    p.neg_tile_cells = 0u - tile_cells;
     p.magic = magic;
     p.nparts = (int)((cells + tile_cells - 1) / tile_cells);
-    p.nparts_pad = p.nparts <= 32 ? 32 : p.nparts <= 64 ? 64 : 128;
+    p.nparts_pad = p.nparts <= 32 ? 32 : 64;
     p.grid = static_cast<unsigned long long *>(a.grid);
 
     const long long batch = std::min<long long>(bp.nrows, 1ll << 30);
@@ -629,6 +647,8 @@ int try_launch_ringcount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
         p.nlists_w = (unsigned)w; // the last batch may launch fewer warps; its lists are the first w rows of head[] / len[]
         k_ring_count<<<ctx->sm_count, kCountThreads, hist_bytes, st>>>(p);
         B200_CUDA(cudaGetLastError());
+        slot->ring_len = p.len, slot->ring_ctl = p.ctl, slot->ring_lists = (size_t)w * p.nparts_pad;
+        slot->ring_rows = (uint64_t)p.nrows, slot->ring_memset_bytes = zero_end + (ff_end - off_head), slot->ring_chunk_entries = 1u << cshift;
     }
     *taken = true;
     return B200_OK;
