@@ -27,7 +27,10 @@
 // HBM traffic: 8 B/row of columns + 2 B/row written + 2 B/row read.  Exact integer counts, same grid layout, any distribution:
 // a ring that fills up inside one 256-row group (> 32 rows of a warp in one part on top of a full leftover) sends the excess rows
 // to direct REDs.
+#include <math.h>
+
 #include <algorithm>
+#include <type_traits>
 
 #include "binby.cuh"
 #include "device_utils.cuh"
@@ -40,6 +43,7 @@ struct RingParams {
     unsigned bins[3];
     unsigned stride[3];
     unsigned stride_sum;          // sum(stride): bin_cell_m1 returns cell - 1
+    float clamp_lo[3], clamp_hi[3]; // CLAMPED variant (fp32 keys): see bin_cell_m2_clamped
     long long row0, nrows;        // this batch
     unsigned cells;
     unsigned tile_cells;          // cells per part (<= 49151): part = idx / tile_cells, local = idx % tile_cells < 2^16
@@ -63,7 +67,11 @@ namespace {
 
 constexpr int kGroupRows = 256;   // rows between two ring flushes: 8 per lane
 constexpr int kGran = 16;         // entries per lane and step in k_ring_count
-constexpr unsigned kLine = 64;    // entries a ring flush moves = one 128-byte line
+#ifndef B200_RING_LINE
+#define B200_RING_LINE 64
+#endif
+constexpr unsigned kLine = B200_RING_LINE; // entries a ring flush moves: 32 = 64 bytes (two sectors), 64 = one 128-byte line
+constexpr int kLineLanes = kLine / 8;      // lanes that move one line with 16 bytes each
 constexpr unsigned kSuper = 32;   // chunks a warp reserves from the pool at a time
 constexpr unsigned kMaxTileCells = 49151; // 192 KB of u32 counters in k_ring_count, one of them the pad cell
 constexpr int kMaxParts = 64;
@@ -99,11 +107,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <typename T>
-__device__ __forceinline__ void lds4(const T *buf, int i, double out[4]);
+__device__ __forceinline__ void lds4(const T *buf, int i, T out[4]);
 template <>
-__device__ __forceinline__ void lds4<float>(const float *buf, int i, double out[4]) {
+__device__ __forceinline__ void lds4<float>(const float *buf, int i, float out[4]) {
     const float4 a = *reinterpret_cast<const float4 *>(buf + i);
-    out[0] = (double)a.x, out[1] = (double)a.y, out[2] = (double)a.z, out[3] = (double)a.w;
+    out[0] = a.x, out[1] = a.y, out[2] = a.z, out[3] = a.w;
 }
 template <>
 __device__ __forceinline__ void lds4<double>(const double *buf, int i, double out[4]) {
@@ -111,11 +119,11 @@ __device__ __forceinline__ void lds4<double>(const double *buf, int i, double ou
     out[0] = a.x, out[1] = a.y, out[2] = b.x, out[3] = b.y;
 }
 template <typename T>
-__device__ __forceinline__ void ldg4(const void *p, long long i, double out[4]);
+__device__ __forceinline__ void ldg4(const void *p, long long i, T out[4]);
 template <>
-__device__ __forceinline__ void ldg4<float>(const void *p, long long i, double out[4]) {
+__device__ __forceinline__ void ldg4<float>(const void *p, long long i, float out[4]) {
     const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(static_cast<const float *>(p) + i));
-    out[0] = (double)__uint_as_float(a.x), out[1] = (double)__uint_as_float(a.y), out[2] = (double)__uint_as_float(a.z), out[3] = (double)__uint_as_float(a.w);
+    out[0] = __uint_as_float(a.x), out[1] = __uint_as_float(a.y), out[2] = __uint_as_float(a.z), out[3] = __uint_as_float(a.w);
 }
 template <>
 __device__ __forceinline__ void ldg4<double>(const void *p, long long i, double out[4]) {
@@ -125,51 +133,85 @@ __device__ __forceinline__ void ldg4<double>(const void *p, long long i, double 
     out[2] = __longlong_as_double(((long long)b.y << 32) | b.x), out[3] = __longlong_as_double(((long long)b.w << 32) | b.z);
 }
 
-// one group of 256 rows (8 per lane): bit-exact index, part, ONE shared-memory atomic for the slot, one 16-bit store.
-// STAGED: the columns sit in shared memory (TMA), every row exists.  Otherwise: global loads with bounds (the ragged last tile).
-// Returns the largest slot a row of this lane was given (>= RING: that row did not fit, see `overflow`); slots[] = kNone marks
-// rows that do not exist.
-template <typename T, int ND, int RING, int RSTRIDE, bool STAGED>
-__device__ __forceinline__ unsigned group_rows(const RingParams &p, const T *buf, int col_stride, long long gbase, long long tend, int lane, unsigned *cnt,
-                                               unsigned short *ring, unsigned idx[8], unsigned slots[8]) {
+// CLAMPED index for fp32 keys: halves the load on the conversion pipe (XU: 16 lanes/clk/SM, the busiest pipe of this kernel at 52 %
+// with F2F.F64.F32 + F2I.F64 per key, profiles/r02_ncu_ring_v3.txt).  The cell is a monotone function of the key (every step of
+// the reference formula is monotone and correctly rounded).  The host finds by bisection over the fp32 values
+//   clamp_lo = the largest fp32 whose cell is 1 (underflow), clamp_hi = the smallest fp32 whose cell is bins+2 (overflow)
+// and checks floor(t(clamp_lo)) == -1 and floor(t(clamp_hi)) == bins with the reference formula.  Then for every non-NaN key
+// v' = min(max(v, clamp_lo), clamp_hi) has the same cell as v and -1 <= floor(t(v')) <= bins, so no integer clamp is needed and
+// the floor can be taken with one round-down addition of 1.5 * 2^52 (low word of the sum) instead of a conversion.
+// Returns cell - 2; NaN -> -2.
+__device__ __forceinline__ int bin_cell_m2_clamped(float v, float lo, float hi, double vmin, double scale, double bins_d) {
+    const float vc = fminf(fmaxf(v, lo), hi); // NaN -> lo (replaced below)
+    const double t = __dmul_rn(__dmul_rn(__dsub_rn((double)vc, vmin), scale), bins_d);
+    const int i = __double2loint(__dadd_rd(t, 6755399441055744.0));
+    return v != v ? -2 : i;
+}
+
+// one row: bit-exact index, part, ONE shared-memory atomic for the slot, one 16-bit store
+template <typename T, int ND, int RING, int RSTRIDE, bool CLAMPED>
+__device__ __forceinline__ void place_row(const RingParams &p, const T (&v)[ND], unsigned *cnt, unsigned short *ring, unsigned &idx, unsigned &slot_out,
+                                          unsigned &worst) {
+    unsigned id;
+    if constexpr (CLAMPED) {
+        id = 2 * p.stride_sum;
+#pragma unroll
+        for (int d = 0; d < ND; d++)
+            id += (unsigned)bin_cell_m2_clamped(v[d], p.clamp_lo[d], p.clamp_hi[d], p.vmin[d], p.scale[d], p.bins_d[d]) * p.stride[d];
+    } else {
+        id = p.stride_sum;
+#pragma unroll
+        for (int d = 0; d < ND; d++)
+            id += (unsigned)bin_cell_m1((double)v[d], p.vmin[d], p.scale[d], p.bins_d[d], p.bins[d]) * p.stride[d];
+    }
+    idx = id;
+    const unsigned part = __umulhi(id, p.magic);
+    const unsigned slot = atomicAdd(cnt + part, 1u);
+    slot_out = slot;
+    worst = max(worst, slot);
+    if (slot < (unsigned)RING)
+        ring[part * RSTRIDE + slot] = (unsigned short)(id + part * p.neg_tile_cells);
+}
+
+// one group of 256 rows (8 per lane) whose keys the caller already holds in registers (loaded one group ahead).
+// Returns the largest slot a row of this lane was given (>= RING: that row did not fit, see `overflow`).
+template <typename T, int ND, int RING, int RSTRIDE, bool CLAMPED>
+__device__ __forceinline__ unsigned group_rows_regs(const RingParams &p, const T (&c)[2][ND][4], unsigned *cnt, unsigned short *ring, unsigned idx[8],
+                                                    unsigned slots[8]) {
     unsigned worst = 0;
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        double c[ND][4];
-        const int r0 = q * 128 + lane * 4;
-        if (STAGED) {
-#pragma unroll
-            for (int d = 0; d < ND; d++)
-                lds4<T>(buf + d * col_stride, r0, c[d]);
-        } else if (gbase + r0 + 4 <= tend) {
-#pragma unroll
-            for (int d = 0; d < ND; d++)
-                ldg4<T>(p.x[d], gbase + r0, c[d]);
-        } else {
-#pragma unroll
-            for (int d = 0; d < ND; d++)
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    c[d][j] = gbase + r0 + j < tend ? (double)__ldcs(static_cast<const T *>(p.x[d]) + gbase + r0 + j) : 0.0;
-        }
+    for (int q = 0; q < 2; q++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            unsigned id = p.stride_sum;
+            T v[ND];
 #pragma unroll
             for (int d = 0; d < ND; d++)
-                id += (unsigned)bin_cell_m1(c[d][j], p.vmin[d], p.scale[d], p.bins_d[d], p.bins[d]) * p.stride[d];
-            idx[q * 4 + j] = id;
+                v[d] = c[q][d][j];
+            place_row<T, ND, RING, RSTRIDE, CLAMPED>(p, v, cnt, ring, idx[q * 4 + j], slots[q * 4 + j], worst);
+        }
+    return worst;
+}
+
+// the ragged end of the batch: global loads with bounds; slots[] = kNone marks rows that do not exist
+template <typename T, int ND, int RING, int RSTRIDE, bool CLAMPED>
+__device__ __forceinline__ unsigned group_rows_tail(const RingParams &p, long long gbase, long long tend, int lane, unsigned *cnt, unsigned short *ring,
+                                                    unsigned idx[8], unsigned slots[8]) {
+    unsigned worst = 0;
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long long row = gbase + q * 128 + lane * 4 + j;
+            idx[q * 4 + j] = 0;
             slots[q * 4 + j] = kNone;
-            if (STAGED || gbase + r0 + j < tend) {
-                const unsigned part = __umulhi(id, p.magic);
-                const unsigned slot = atomicAdd(cnt + part, 1u);
-                slots[q * 4 + j] = slot;
-                worst = max(worst, slot);
-                if (slot < (unsigned)RING)
-                    ring[part * RSTRIDE + slot] = (unsigned short)(id + part * p.neg_tile_cells);
+            if (row < tend) {
+                T v[ND];
+#pragma unroll
+                for (int d = 0; d < ND; d++)
+                    v[d] = __ldcs(static_cast<const T *>(p.x[d]) + row);
+                place_row<T, ND, RING, RSTRIDE, CLAMPED>(p, v, cnt, ring, idx[q * 4 + j], slots[q * 4 + j], worst);
             }
         }
-    }
     return worst;
 }
 
@@ -180,11 +222,11 @@ __device__ __forceinline__ unsigned group_rows(const RingParams &p, const T *buf
 template <typename T, int ND, int PPL, int FG>
 struct RingLayout {
     static constexpr int kTileRows = kGroupRows * FG;
-    static constexpr int kRing = 96;
+    static constexpr int kRing = kLine == 64 ? 96 : 64;
     static constexpr int kRingStride = kRing + 8; // 208 bytes: 16-byte aligned rows that rotate over the banks
-    static constexpr size_t kColBytes = 2ull * ND * kTileRows * sizeof(T);
+    static constexpr size_t kColBytes = 0; // the keys travel through registers
     static constexpr size_t kRingBytes = 32ull * PPL * kRingStride * 2;
-    static constexpr size_t kCntBytes = 32ull * PPL * 4;
+    static constexpr size_t kCntBytes = 32ull * PPL * 4 + 256; // + the flush's (write position, owner) map
     static constexpr size_t kPerWarp = kColBytes + kRingBytes + kCntBytes;
 };
 
@@ -197,32 +239,24 @@ struct Owner {
     unsigned total[PPL]; // entries written to this list so far
 };
 
-template <typename T, int ND, int PPL, int FG, int WARPS>
+template <typename T, int ND, int PPL, int FG, int WARPS, bool CLAMPED>
 __global__ void __launch_bounds__(WARPS * 32, 2) k_ring_partition(const __grid_constant__ RingParams p) {
     using L = RingLayout<T, ND, PPL, FG>;
     constexpr int RING = L::kRing, RSTRIDE = L::kRingStride;
-    static_assert(RING - kLine <= 32 && (RSTRIDE * 2) % 16 == 0, "ring geometry");
-    constexpr int TILE = L::kTileRows;
+    static_assert(RING - kLine <= kLine && (RSTRIDE * 2) % 16 == 0, "ring geometry");
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    __shared__ __align__(8) unsigned long long bars[WARPS][2];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *mine = dyn_smem + (size_t)warp * L::kPerWarp;
-    T *const cols = reinterpret_cast<T *>(mine);                                         // [2][ND][TILE]
     unsigned short *const ring = reinterpret_cast<unsigned short *>(mine + L::kColBytes); // [32*PPL][RING + 8]
     unsigned *const cnt = reinterpret_cast<unsigned *>(mine + L::kColBytes + L::kRingBytes);
-    if (lane == 0) {
-        mbar_init(&bars[warp][0], 1);
-        mbar_init(&bars[warp][1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    uint2 *const fmap = reinterpret_cast<uint2 *>(cnt + 32 * PPL); // [32] {pool entry index, owner lane} of the lines of one flush
 #pragma unroll
     for (int k = 0; k < PPL; k++)
         cnt[lane + 32 * k] = 0;
     __syncwarp();
 
     const unsigned cshift = p.chunk_shift, csize = 1u << cshift;
-    const long long nfull = p.nrows / TILE; // tiles [0, nfull) are complete and TMA staged; the ragged rest is one more tile
     const long long wglobal = (long long)blockIdx.x * WARPS + warp, wtotal = (long long)gridDim.x * WARPS;
 
     Owner<PPL> own;
@@ -292,29 +326,27 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_ring_partition(const __grid_c
                 }
                 cnt[part] = n - kLine;
             }
-            unsigned m = __ballot_sync(0xffffffffu, has);
-            const int quarter = lane >> 3, ql = lane & 7;
-            while (m) {
-                int src = -1;
-#pragma unroll
-                for (int j = 0; j < 4; j++) { // the j-th lowest owner with a line goes to quarter-warp j
-                    const int bit = m ? __ffs(m) - 1 : -1;
-                    if (j == quarter)
-                        src = bit;
-                    m &= m - 1; // 0 stays 0
-                }
-                const unsigned wps = __shfl_sync(0xffffffffu, wp, src < 0 ? 0 : src);
-                if (src >= 0) {
-                    uint4 *r = reinterpret_cast<uint4 *>(ring + (src + 32 * k) * RSTRIDE);
-                    const uint4 w = r[ql];
+            // the owners publish {write position, lane} in rank order; then every group of kLineLanes lanes moves one line
+            const unsigned m = __ballot_sync(0xffffffffu, has);
+            if (m) {
+                const int nl = __popc(m);
+                if (has)
+                    fmap[__popc(m & ((1u << lane) - 1u))] = make_uint2(wp, (unsigned)lane);
+                __syncwarp();
+                const int grp = lane / kLineLanes, gl = lane % kLineLanes;
+                for (int j = grp; j < nl; j += 32 / kLineLanes) {
+                    const uint2 e = fmap[j];
+                    uint4 *r = reinterpret_cast<uint4 *>(ring + (e.y + 32 * k) * RSTRIDE);
+                    const uint4 w = r[gl];
                     uint4 up = make_uint4(0, 0, 0, 0);
-                    if (ql < (RING - kLine) / 8)
-                        up = r[kLine / 8 + ql];
-                    if (wps != kNone)
-                        reinterpret_cast<uint4 *>(p.pool + wps)[ql] = w;
-                    if (ql < (RING - kLine) / 8)
-                        r[ql] = up; // the entries behind the line slide to the front (each lane rewrites the 16 bytes it read)
+                    if (gl < (RING - (int)kLine) / 8)
+                        up = r[kLineLanes + gl];
+                    if (e.x != kNone)
+                        reinterpret_cast<uint4 *>(p.pool + e.x)[gl] = w;
+                    if (gl < (RING - (int)kLine) / 8)
+                        r[gl] = up; // the entries behind the line slide to the front (each lane rewrites the 16 bytes it read)
                 }
+                __syncwarp();
             }
         }
     };
@@ -326,52 +358,55 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_ring_partition(const __grid_c
                 atomicAdd(p.grid + idx[r], 1ull);
     };
 
-    // ---- complete tiles: columns staged by TMA, double buffered ---------------------------------------------------------------
-    const unsigned bar0 = smem_u32(&bars[warp][0]);
-    const unsigned col0 = smem_u32(cols);
-    constexpr unsigned kStageBytes = ND * TILE * sizeof(T), kColTileBytes = TILE * sizeof(T);
-    auto issue = [&](long long t, unsigned st) { // lane 0: start the bulk copies of tile t's columns into stage st
-        const unsigned bar = bar0 + 8 * st;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kStageBytes) : "memory");
+    // ---- complete groups of 256 rows: the keys of the NEXT group are loaded into registers (128-bit, evict-first) while the
+    // current one is placed: two register sets, the loop is unrolled by two so that no copy is needed.  (A TMA-staged variant
+    // spent 8.5 of its 56 warp instructions per 32 rows on issuing the bulk copies and waiting on the mbarriers, and 4 KB of shared
+    // memory per warp on the double buffer: profiles/r02_ncu_ring_v4.txt.)
+    const long long ngroups = p.nrows / kGroupRows;
+    auto load = [&](long long g, T (&dst)[2][ND][4]) {
+        const long long r0 = p.row0 + g * kGroupRows + lane * 4;
 #pragma unroll
-        for (int d = 0; d < ND; d++)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(col0 + st * kStageBytes + d * kColTileBytes),
-                         "l"(static_cast<const T *>(p.x[d]) + p.row0 + t * TILE), "r"(kColTileBytes), "r"(bar)
-                         : "memory");
+        for (int q = 0; q < 2; q++)
+#pragma unroll
+            for (int d = 0; d < ND; d++)
+                ldg4<T>(p.x[d], r0 + q * 128, dst[q][d]);
     };
-    unsigned it = 0; // tiles this warp has consumed: stage = it & 1, mbarrier parity = (it >> 1) & 1
-    if (lane == 0 && wglobal < nfull)
-        issue(wglobal, 0);
-    for (long long tile = wglobal; tile < nfull; tile += wtotal, it++) {
-        const unsigned st = it & 1;
-        if (lane == 0 && tile + wtotal < nfull)
-            issue(tile + wtotal, st ^ 1); // prefetch the next tile while this one is processed
-        mbar_wait(&bars[warp][st], (it >> 1) & 1);
-        const T *buf = cols + st * ND * TILE;
-#pragma unroll 1
-        for (int grp = 0; grp < FG; grp++) {
-            unsigned idx[8], slots[8];
-            const unsigned worst = group_rows<T, ND, RING, RSTRIDE, true>(p, buf + grp * kGroupRows, TILE, 0, 0, lane, cnt, ring, idx, slots);
-            __syncwarp();
-            flush(false);
-            if (__any_sync(0xffffffffu, worst >= (unsigned)RING))
-                overflow(idx, slots);
-            __syncwarp();
+    auto place = [&](const T (&c)[2][ND][4]) {
+        unsigned idx[8], slots[8];
+        const unsigned worst = group_rows_regs<T, ND, RING, RSTRIDE, CLAMPED>(p, c, cnt, ring, idx, slots);
+        __syncwarp();
+        flush(false);
+        if (__any_sync(0xffffffffu, worst >= (unsigned)RING))
+            overflow(idx, slots);
+        __syncwarp();
+    };
+    {
+        T ca[2][ND][4], cb[2][ND][4];
+        long long g = wglobal;
+        if (g < ngroups)
+            load(g, ca);
+        while (g < ngroups) {
+            if (g + wtotal < ngroups)
+                load(g + wtotal, cb);
+            place(ca);
+            g += wtotal;
+            if (g >= ngroups)
+                break;
+            if (g + wtotal < ngroups)
+                load(g + wtotal, ca);
+            place(cb);
+            g += wtotal;
         }
-        fence_proxy_async(); // our generic-proxy reads of this stage are done before the copy engine refills it
     }
-    // ---- the ragged last tile (global loads with bounds), taken by the warp whose turn it is -------------------------------------
-    if (nfull * TILE < p.nrows && nfull % wtotal == wglobal) {
-        const long long tbase = p.row0 + nfull * TILE, tend = p.row0 + p.nrows;
-        for (int grp = 0; tbase + grp * kGroupRows < tend; grp++) {
-            unsigned idx[8], slots[8];
-            const unsigned worst = group_rows<T, ND, RING, RSTRIDE, false>(p, nullptr, 0, tbase + grp * kGroupRows, tend, lane, cnt, ring, idx, slots);
-            __syncwarp();
-            flush(false);
-            if (__any_sync(0xffffffffu, worst >= (unsigned)RING))
-                overflow(idx, slots);
-            __syncwarp();
-        }
+    // ---- the ragged end (< 256 rows), taken by the warp whose turn it is ------------------------------------------------------------
+    if (ngroups * kGroupRows < p.nrows && ngroups % wtotal == wglobal) {
+        unsigned idx[8], slots[8];
+        const unsigned worst = group_rows_tail<T, ND, RING, RSTRIDE, CLAMPED>(p, p.row0 + ngroups * kGroupRows, p.row0 + p.nrows, lane, cnt, ring, idx, slots);
+        __syncwarp();
+        flush(false);
+        if (__any_sync(0xffffffffu, worst >= (unsigned)RING))
+            overflow(idx, slots);
+        __syncwarp();
     }
     // ---- the incomplete last lines, then the list descriptors ---------------------------------------------------------------
     flush(true);
@@ -475,20 +510,20 @@ __global__ void __launch_bounds__(kCountThreads, 1) k_ring_count(const __grid_co
 }
 
 template <typename T, int ND, int PPL, int FG>
-int launch_partition_cfg(int sm_count, cudaStream_t st, RingParams &p, int *warps_out, bool dry) {
+int launch_partition_cfg(int sm_count, cudaStream_t st, RingParams &p, int *warps_out, bool dry, bool clamped) {
     using L = RingLayout<T, ND, PPL, FG>;
     constexpr int fit = (int)((113 * 1024 - 512) / L::kPerWarp); // two CTAs per SM
-    constexpr int WARPS = fit > 16 ? 16 : fit;
+    constexpr int WARPS = fit > 12 ? 12 : fit; // 24 warps per SM leave 85 registers per thread: the two key sets + the placement fit without spills
     if constexpr (WARPS >= 2) {
-        const long long ntiles = (p.nrows + L::kTileRows - 1) / L::kTileRows;
-        // at least ~8 tiles per warp so that the per-(warp, part) partial chunks stay a small share of the scratch
-        long long blocks = std::min<long long>((ntiles / 8 + WARPS - 1) / WARPS, (long long)sm_count * 2);
+        const long long ngroups = (p.nrows + kGroupRows - 1) / kGroupRows;
+        // at least ~8 groups per warp so that the per-(warp, part) partial chunks stay a small share of the scratch
+        long long blocks = std::min<long long>((ngroups / 8 + WARPS - 1) / WARPS, (long long)sm_count * 2);
         if (blocks < 1)
             blocks = 1;
         *warps_out = (int)blocks * WARPS;
         if (dry)
             return B200_OK;
-        auto kern = k_ring_partition<T, ND, PPL, FG, WARPS>;
+        auto kern = clamped ? k_ring_partition<T, ND, PPL, FG, WARPS, std::is_same<T, float>::value> : k_ring_partition<T, ND, PPL, FG, WARPS, false>;
         constexpr size_t dyn = L::kPerWarp * WARPS;
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         kern<<<(int)blocks, WARPS * 32, dyn, st>>>(p);
@@ -501,20 +536,80 @@ int launch_partition_cfg(int sm_count, cudaStream_t st, RingParams &p, int *warp
 }
 
 template <typename T, int ND>
-int launch_partition_nd(int sm_count, cudaStream_t st, RingParams &p, int fg, int *warps_out, bool dry) {
-    const int ppl = p.nparts_pad / 32;
-    if (ppl == 1)
-        return fg == 2 ? launch_partition_cfg<T, ND, 1, 2>(sm_count, st, p, warps_out, dry) : launch_partition_cfg<T, ND, 1, 1>(sm_count, st, p, warps_out, dry);
-    return launch_partition_cfg<T, ND, 2, 1>(sm_count, st, p, warps_out, dry);
+int launch_partition_nd(int sm_count, cudaStream_t st, RingParams &p, int *warps_out, bool dry, bool clamped) {
+    if (p.nparts_pad == 32)
+        return launch_partition_cfg<T, ND, 1, 1>(sm_count, st, p, warps_out, dry, clamped);
+    return launch_partition_cfg<T, ND, 2, 1>(sm_count, st, p, warps_out, dry, clamped);
 }
 
 template <typename T>
-int launch_partition(int nd, int sm_count, cudaStream_t st, RingParams &p, int fg, int *warps_out, bool dry) {
+int launch_partition(int nd, int sm_count, cudaStream_t st, RingParams &p, int *warps_out, bool dry, bool clamped) {
     switch (nd) {
-    case 1: return launch_partition_nd<T, 1>(sm_count, st, p, fg, warps_out, dry);
-    case 2: return launch_partition_nd<T, 2>(sm_count, st, p, fg, warps_out, dry);
-    default: return launch_partition_nd<T, 3>(sm_count, st, p, fg, warps_out, dry);
+    case 1: return launch_partition_nd<T, 1>(sm_count, st, p, warps_out, dry, clamped);
+    case 2: return launch_partition_nd<T, 2>(sm_count, st, p, warps_out, dry, clamped);
+    default: return launch_partition_nd<T, 3>(sm_count, st, p, warps_out, dry, clamped);
     }
+}
+
+// ---- host side of the CLAMPED index (see bin_cell_m2_clamped) ---------------------------------------------------------------
+// the reference formula, evaluated exactly like src/binners.cpp:13-57 does (IEEE double, no contraction: volatile keeps every
+// intermediate rounded to double whatever the host compiler flags)
+double ref_t(float v, double vmin, double scale, double bins_d) {
+    volatile double d = (double)v - vmin;
+    volatile double s = d * scale;
+    volatile double t = s * bins_d;
+    return t;
+}
+// cell of a non-NaN key
+long long ref_cell(float v, double vmin, double scale, double bins_d, unsigned bins) {
+    volatile double d = (double)v - vmin;
+    volatile double s = d * scale;
+    if (s < 0)
+        return 1;
+    if (s >= 1)
+        return (long long)bins + 2;
+    volatile double t = s * bins_d;
+    return (long long)(int)t + 2;
+}
+// fp32 values in increasing order <-> integers in increasing order (-inf .. +inf, NaNs excluded)
+int float_order(float f) {
+    int b;
+    memcpy(&b, &f, 4);
+    return b >= 0 ? b : (int)(0x80000000u - (unsigned)b);
+}
+float order_float(int o) {
+    const int b = o >= 0 ? o : (int)(0x80000000u - (unsigned)o);
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
+// the clamp bounds of one dimension; false when the construction does not apply (then the plain index runs)
+bool clamp_bounds(double vmin, double scale, double bins_d, unsigned bins, float *lo_out, float *hi_out) {
+    const int omin = float_order(-INFINITY), omax = float_order(INFINITY);
+    auto first_with_cell_at_least = [&](long long c) { // smallest order o in [omin, omax] with cell >= c; omax + 1 if none
+        long long lo = omin, hi = (long long)omax + 1;
+        while (lo < hi) {
+            const long long mid = lo + (hi - lo) / 2;
+            if (ref_cell(order_float((int)mid), vmin, scale, bins_d, bins) >= c)
+                hi = mid;
+            else
+                lo = mid + 1;
+        }
+        return lo;
+    };
+    const long long o_in = first_with_cell_at_least(2), o_over = first_with_cell_at_least((long long)bins + 2);
+    if (o_in <= omin || o_over > omax || o_in >= o_over)
+        return false; // no underflow value, no overflow value, or no value in range
+    const float lo = order_float((int)(o_in - 1)), hi = order_float((int)o_over);
+    if (!(lo > -INFINITY) || !(hi < INFINITY))
+        return false;
+    const double tlo = ref_t(lo, vmin, scale, bins_d), thi = ref_t(hi, vmin, scale, bins_d);
+    // floor(t(lo)) == -1 and floor(t(hi)) == bins: every clamped key then has -1 <= floor(t) <= bins by monotonicity
+    if (!(tlo >= -1.0 && tlo < 0.0) || !(thi >= bins_d && thi < bins_d + 1.0))
+        return false;
+    *lo_out = lo;
+    *hi_out = hi;
+    return true;
 }
 
 // part == __umulhi(idx, magic) for all idx < cells?  Both sides are monotone step functions of idx, so it suffices to check the
@@ -534,7 +629,7 @@ bool magic_exact(unsigned cells, unsigned tile_cells, unsigned magic) {
 int try_launch_ringcount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool vec, bool *taken) {
     *taken = false;
     static const bool disabled = getenv("B200_DISABLE_TILECOUNT") && atoi(getenv("B200_DISABLE_TILECOUNT")) != 0;
-    static const int fg = getenv("B200_RING_FG") ? atoi(getenv("B200_RING_FG")) : 1;
+    static const bool no_clamp = getenv("B200_RING_NO_CLAMP") && atoi(getenv("B200_RING_NO_CLAMP")) != 0; // A/B knob
     if (disabled || !vec || bp.nb < 1 || bp.nb > 3 || bp.na != 1 || bp.nrows < (1ll << 22))
         return B200_OK;
     const DevAgg &a = bp.a[0];
@@ -560,6 +655,9 @@ int try_launch_ringcount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
         p.stride[i] = (unsigned)b.stride;
         p.stride_sum += (unsigned)b.stride;
     }
+    bool clamped = t == B200_F32 && !no_clamp;
+    for (int i = 0; i < bp.nb && clamped; i++)
+        clamped = clamp_bounds(p.vmin[i], p.scale[i], p.bins_d[i], p.bins[i], &p.clamp_lo[i], &p.clamp_hi[i]);
     // as few parts as possible (32, else 64, else 128): the ring memory of k_ring_partition scales with the parts per lane;
     // tile_cells is nudged upwards until the one-instruction division is exact
     unsigned tile_cells = 0, magic = 0;
@@ -589,9 +687,9 @@ int try_launch_ringcount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
     p.nrows = batch;
     int nwarps = 0;
     if (t == B200_F32)
-        B200_CHECK(launch_partition<float>(bp.nb, ctx->sm_count, nullptr, p, fg, &nwarps, true));
+        B200_CHECK(launch_partition<float>(bp.nb, ctx->sm_count, nullptr, p, &nwarps, true, clamped));
     else
-        B200_CHECK(launch_partition<double>(bp.nb, ctx->sm_count, nullptr, p, fg, &nwarps, true));
+        B200_CHECK(launch_partition<double>(bp.nb, ctx->sm_count, nullptr, p, &nwarps, true, false));
     if (nwarps <= 0)
         return B200_OK;
     // chunk size: about a quarter of a (warp, part) list, within 512..2048 entries
@@ -641,9 +739,9 @@ int try_launch_ringcount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
         B200_CUDA(cudaMemsetAsync(base + off_head, 0xFF, ff_end - off_head, st));
         int w = 0;
         if (t == B200_F32)
-            B200_CHECK(launch_partition<float>(bp.nb, ctx->sm_count, st, p, fg, &w, false));
+            B200_CHECK(launch_partition<float>(bp.nb, ctx->sm_count, st, p, &w, false, clamped));
         else
-            B200_CHECK(launch_partition<double>(bp.nb, ctx->sm_count, st, p, fg, &w, false));
+            B200_CHECK(launch_partition<double>(bp.nb, ctx->sm_count, st, p, &w, false, false));
         p.nlists_w = (unsigned)w; // the last batch may launch fewer warps; its lists are the first w rows of head[] / len[]
         k_ring_count<<<ctx->sm_count, kCountThreads, hist_bytes, st>>>(p);
         B200_CUDA(cudaGetLastError());
