@@ -36,10 +36,12 @@ def parse():
     ap.add_argument("--e2e-rows", type=float, default=float(1 << 28), help="rows per GPU per step of the host-buffer (e2e) leg")
     ap.add_argument("--e2e-chunk", type=float, default=float(1 << 24))
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-threads", type=int, default=16, help="Python feeder threads of the e2e leg (the executor's thread pool)")
     ap.add_argument("--cpu-rows", type=float, default=0, help="rows of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--extra", action="store_true", help="also time the other BASELINE.json configs (sum, 3-D mean+std, groupby)")
+    ap.add_argument("--no-also", action="store_true", help="skip the other BASELINE.json configs (sum, 3-D mean+std, groupby)")
+    ap.add_argument("--also-sample", type=float, default=1e8, help="rows of the parity sample of each `also` config against oracle/_ref")
     return ap.parse_args()
 
 
@@ -47,9 +49,10 @@ def parse():
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons with NVML during the timed region (B200_PROFILING.md clocks line)."""
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.005):
         super().__init__(daemon=True)
         self.index = index
+        self.period = period
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
@@ -83,7 +86,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                if self.stop_flag.wait(0.005):
+                if self.stop_flag.wait(self.period):
                     break
         except Exception as e:
             self.err = repr(e)
@@ -176,6 +179,254 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def timed_ms(stream, ctx, fn, reps):
+    """mean device time of `fn` (launches on the slot stream) over `reps` runs after one warm-up; CUDA events on that stream"""
+    import torch
+    fn()
+    ctx.sync(0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    ctx.sync(0)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def also_configs(args, ctx, stream, gen, peak, rows, nthreads):
+    """BASELINE.json configs[1..3] at full size (device-resident, timed with CUDA events) + a parity check of the first
+    `--also-sample` rows against the compiled, unmodified reference (oracle/_ref) run on the host cores."""
+    import numpy as np
+    import torch
+    from oracle import oracle as O, ref_driver as R
+    from vaex_b200 import superagg, superutils
+    out = {}
+    ns = int(min(args.also_sample, rows))
+    have_ref = R.available()
+
+    def entry(ms, bytes_per_row, kernel, parity, **extra):
+        gbs = bytes_per_row * rows / (ms * 1e-3) / 1e9
+        return dict(rows=rows, rows_per_s=rows / (ms * 1e-3), ms_per_step=ms, algorithmic_bytes_per_row=bytes_per_row, achieved_gbs=gbs,
+                    frac=gbs / peak, kernel=kernel, parity=parity, parity_against="oracle/_ref (compiled reference), %d threads" % nthreads if have_ref else "unavailable",
+                    parity_rows=ns, **extra)
+
+    # ---- configs[1]: df.sum(z, binby=[x,y], shape=1024) on fp32 ---------------------------------------------------------------
+    x = torch.empty(rows, dtype=torch.float32, device="cuda").normal_(generator=gen)
+    y = torch.empty(rows, dtype=torch.float32, device="cuda").normal_(generator=gen)
+    z = torch.empty(rows, dtype=torch.float32, device="cuda").normal_(generator=gen)
+    bx = superagg.BinnerScalar_float32(1, "x", LIMITS[0], LIMITS[1], SHAPE)
+    by = superagg.BinnerScalar_float32(1, "y", LIMITS[0], LIMITS[1], SHAPE)
+    grid = superagg.Grid([bx, by])
+    asum = superagg.AggSum_float32(grid, 1, 1)
+
+    def bind(n):
+        bx.set_data(0, x[:n])
+        by.set_data(0, y[:n])
+        asum.set_data(0, z[:n], 0)
+
+    def c2():
+        asum.reset(0)
+        grid.bin(0, [asum], rows)
+    bind(rows)
+    ms = timed_ms(stream, ctx, c2, 3)
+    parity = None
+    if have_ref:
+        bind(ns)
+        asum.reset(0)
+        grid.bin(0, [asum], ns)
+        got = asum.get_result()
+        xc, yc, zc = (t[:ns].cpu().numpy() for t in (x, y, z))
+        want = R.RefBinby([O.scalar(xc, LIMITS[0], LIMITS[1], SHAPE), O.scalar(yc, LIMITS[0], LIMITS[1], SHAPE)], [O.agg("sum", zc)], nthreads).run(ns)[0]
+        parity = bool(np.allclose(got, want, rtol=1e-6, atol=1e-9 * float(np.abs(want).max())))
+    out["configs[1] df.sum(z, binby=[x,y], shape=1024), 1e9 fp32 rows"] = entry(ms, 12, "k_binby_fast<float,2,float> (one RED.ADD.F64 per row)", parity, tolerance="rtol 1e-6")
+    del x, y, z, bx, by, grid, asum
+    torch.cuda.empty_cache()
+
+    # ---- configs[2]: df.mean(v) + df.std(v), binby=[x,y,z], shape=256 on fp64: count, sum, sum^2 fused -----------------------------
+    cols = [torch.empty(rows, dtype=torch.float64, device="cuda").normal_(generator=gen) for _ in range(4)]
+    bs = [superagg.BinnerScalar_float64(1, "xyz"[i], LIMITS[0], LIMITS[1], 256) for i in range(3)]
+    grid = superagg.Grid(bs)
+    aggs = [superagg.AggCount_float64(grid, 1, 1), superagg.AggSum_float64(grid, 1, 1), superagg.AggSumMoment_float64(grid, 1, 1, 2)]
+
+    def bind3(n):
+        for b, c in zip(bs, cols):
+            b.set_data(0, c[:n])
+        for a in aggs:
+            a.set_data(0, cols[3][:n], 0)
+
+    def c3():
+        for a in aggs:
+            a.reset(0)
+        grid.bin(0, aggs, rows)
+    bind3(rows)
+    ms = timed_ms(stream, ctx, c3, 2)
+    parity = None
+    if have_ref:
+        bind3(ns)
+        for a in aggs:
+            a.reset(0)
+        grid.bin(0, aggs, ns)
+        got = [a.get_result() for a in aggs]
+        hc = [c[:ns].cpu().numpy() for c in cols]
+        want = R.RefBinby([O.scalar(hc[i], LIMITS[0], LIMITS[1], 256) for i in range(3)],
+                          [O.agg("count", hc[3]), O.agg("sum", hc[3]), O.agg("sum_moment", hc[3], moment=2)], nthreads).run(ns)
+        parity = bool(np.array_equal(got[0], want[0]) and all(np.allclose(got[k], want[k], rtol=1e-6, atol=1e-9 * float(np.abs(want[k]).max())) for k in (1, 2)))
+        del hc, want
+    out["configs[2] df.mean(v)+df.std(v), binby=[x,y,z], shape=256, 1e9 fp64 rows"] = entry(
+        ms, 32, "k_sort_partition + k_sort_apply (region-sorted scatter, csrc/tilesort.cu)", parity, tolerance="count bit-exact; sum, sum^2 rtol 1e-6", grid_cells=len(grid))
+    del cols, bs, grid, aggs
+    torch.cuda.empty_cache()
+
+    # ---- configs[3]: df.groupby(k).agg({v: [sum, count]}), 1e6 sparse int64 keys ------------------------------------------------
+    keys = torch.randint(0, 1_000_000, (rows,), device="cuda", dtype=torch.int64, generator=gen) * 256 + 5
+    v = torch.empty(rows, dtype=torch.float64, device="cuda").normal_(generator=gen)
+    torch.cuda.synchronize()
+
+    def groupby(n, time_it):
+        k, vv = keys[:n], v[:n]
+        ctx.sync(0)
+        t0 = time.perf_counter()
+        s = superutils.ordered_set_int64(7)
+        s.update(k, -1)
+        nkeys = len(s)  # finalises: ordinals are defined
+        ctx.sync(0)
+        t1 = time.perf_counter() - t0
+        hb = superagg.BinnerHash_int64(1, "k", s)
+        g = superagg.Grid([hb])
+        hb.set_data(0, k)
+        a_sum, a_cnt = superagg.AggSum_float64(g, 1, 1), superagg.AggCount_float64(g, 1, 1)
+        for a in (a_sum, a_cnt):
+            a.set_data(0, vv, 0)
+
+        def p2():
+            a_sum.reset(0)
+            a_cnt.reset(0)
+            g.bin(0, [a_sum, a_cnt], n)
+        ms2 = timed_ms(stream, ctx, p2, 2) if time_it else (p2(), 0.0)[1]
+        return s, nkeys, t1 * 1e3, ms2, a_sum.get_result(), a_cnt.get_result()
+    groupby(rows, False)  # first build grows the table: keep it out of the timing, like the other configs' warm-up
+    s, nkeys, ms1, ms2, _, gcnt = groupby(rows, True)
+    assert int(gcnt.sum()) == rows
+    parity = None
+    if have_ref:
+        s, nk, _, _, gsum, gcnt = groupby(ns, False)
+        gk = s.key_array()
+        hk, hv = keys[:ns].cpu().numpy(), v[:ns].cpu().numpy()
+        rk, rsum, rcnt = R.groupby_sum_count(hk, hv, nthreads)
+        # the reference's ordinals depend on thread timing (SURVEY section 7): compare as key -> (sum, count) maps
+        og, orf = np.argsort(gk), np.argsort(rk)
+        parity = bool(len(gk) == len(rk) and np.array_equal(gk[og], rk[orf]) and np.array_equal(np.asarray(gcnt)[:nk][og], np.asarray(rcnt)[:len(rk)][orf])
+                      and np.allclose(np.asarray(gsum)[:nk][og], np.asarray(rsum)[:len(rk)][orf], rtol=1e-6, atol=1e-9))
+    e = entry(ms1 + ms2, 24, "k_set_insert + finalise (pass 1), fused hash-probe binner k_binby (pass 2)", parity, tolerance="keys and counts bit-exact; sums rtol 1e-6",
+              unique_keys=nkeys, pass1_ms=ms1, pass2_ms=ms2, pass1_note="wall clock incl. finalisation (ordinals defined), table already grown")
+    out["configs[3] df.groupby(k).agg({v:[sum,count]}), 1e6 sparse int64 keys, 1e9 rows"] = e
+    del keys, v
+    torch.cuda.empty_cache()
+    return out
+
+
+def e2e_leg(args, ctx, world, rank, local, x, y, barrier, sampler, out):
+    """End to end through the reference-facing front: PAGEABLE numpy columns -> Frame.count(binby=...) -> chunk-feed loop on T
+    Python threads -> TaskPartAggregation.process(thread_index, i1, i2, ..., blocks) -> b200_bin(HOST) on slot thread_index ->
+    (N>1: NCCL all-reduce) -> numpy result.  Host->device copies of every chunk and the device->host read of the grid are inside
+    the timed region (wall clock, max over ranks).  Timed with vaex's chunk cap (1M rows, vaex/settings.py:85-87) — the headline
+    `value` — and with 16M-row chunks; the pinned + B200_FLAG_ASYNC_HOST figure through the native class protocol (B2) is kept as
+    a third key."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from vaex_b200 import _lib, engine, execution, superagg
+    from vaex_b200.frame import Frame
+    erows = int(args.e2e_rows)
+    xn = x[:erows].cpu().numpy()  # plain pageable host memory, what a numpy / memory-mapped vaex column is
+    yn = y[:erows].cpu().numpy()
+    nthreads = max(1, min(args.e2e_threads, (os.cpu_count() or 8) // max(world, 1)))
+    cells = (SHAPE + 3) ** 2
+    res = {}
+
+    def run(chunk_max, steps):
+        ex = execution.Executor(nthreads=nthreads, chunk_size_max=chunk_max)
+        df = Frame({"x": xn, "y": yn}, executor=ex)
+
+        def one():
+            g = df.count(binby=["x", "y"], limits=[list(LIMITS), list(LIMITS)], shape=SHAPE, edges=True)
+            if world > 1:
+                t = torch.from_numpy(np.ascontiguousarray(g)).cuda()
+                dist.all_reduce(t)
+                g = t.cpu().numpy()
+            return g
+        one()  # warm-up: both bounce buffers of every slot and the arenas are allocated here
+        one()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            g = one()
+        barrier()
+        w = time.perf_counter() - w0
+        if world > 1:
+            t = torch.tensor([w], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            w = float(t.item())
+        assert int(g.sum()) == erows * world, "row conservation failed in the e2e leg"
+        return erows * world * steps / w, ex.chunk_size_for(erows)
+
+    sampler2 = ClockSampler(local, period=0.05)  # NVML queries take driver locks the 16 feeder threads need: poll gently
+    sampler2.start()
+    v1, c1 = run(1 << 20, args.e2e_steps)
+    v16, c16 = run(1 << 24, args.e2e_steps)
+    c2 = sampler2.result()
+    if c2.get("sm_mhz") is not None:  # the e2e steps are a timed region too: fold their clock samples in
+        both = sorted(sampler.samples + sampler2.samples)
+        out["clocks"] = {"sm_mhz": both[len(both) // 2], "sm_max_mhz": c2["sm_max_mhz"], "reasons": sorted(set(out["clocks"]["reasons"]) | set(c2["reasons"])),
+                         "samples": len(both), "windows": "device-resident steps + e2e steps"}
+    res = {"value": v1, "unit": "rows/s", "h2d_bytes_per_step": erows * BYTES_PER_ROW, "d2h_bytes_per_step": cells * 8, "rows_per_step_per_gpu": erows,
+           "chunk_rows": c1, "threads": nthreads,
+           "path": "pageable numpy -> Frame.count -> TaskPartAggregation.process -> b200_bin(HOST): page-locked bounce ring, no per-call sync",
+           "chunks_16M": {"value": v16, "unit": "rows/s", "chunk_rows": c16}}
+
+    # the plumbing ceiling: pinned host columns through the native class protocol with B200_FLAG_ASYNC_HOST on 4 slots
+    bx = superagg.BinnerScalar_float32(4, "x", LIMITS[0], LIMITS[1], SHAPE)
+    by = superagg.BinnerScalar_float32(4, "y", LIMITS[0], LIMITS[1], SHAPE)
+    grid = superagg.Grid([bx, by])
+    agg = superagg.AggCount_int64(grid, 1, 4)
+    host_grid = torch.empty(cells, dtype=torch.int64).pin_memory()
+    xh, yh = torch.from_numpy(xn).pin_memory(), torch.from_numpy(yn).pin_memory()
+    xp, yp = xh.numpy(), yh.numpy()
+    chunk, nslots = int(args.e2e_chunk), 4
+
+    def pinned_step():
+        agg.reset(0)
+        ctx.sync(0)
+        for c, i1 in enumerate(range(0, erows, chunk)):
+            i2 = min(i1 + chunk, erows)
+            sl = c % nslots
+            bx.set_data(sl, xp[i1:i2])
+            by.set_data(sl, yp[i1:i2])
+            grid.bin(sl, [agg], i2 - i1, row_offset=i1, flags=_lib.FLAG_ASYNC_HOST)
+        ctx.sync(-1)
+        if world > 1:
+            engine.all_reduce([agg], slot=0)
+        agg.read_async(0, host_grid)
+        ctx.sync(0)
+    pinned_step()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        pinned_step()
+    barrier()
+    w = time.perf_counter() - w0
+    if world > 1:
+        t = torch.tensor([w], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        w = float(t.item())
+    assert int(host_grid.sum().item()) == erows * world
+    res["pinned_async_b2"] = {"value": erows * world * args.e2e_steps / w, "unit": "rows/s", "chunk_rows": chunk, "slots": nslots,
+                              "note": "pre-pinned host columns -> b200_bin(HOST, ASYNC) on 4 slots: the PCIe ceiling of this path"}
+    return res
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -258,107 +509,45 @@ def run_b200(args):
     assert counted == rows * world, f"row conservation failed: grid holds {counted}, expected {rows * world}"
 
     value = rows * world * args.steps / (total_ms * 1e-3)
-    # count(*) on a 1027^2 grid takes the tile-partition path from 2^22 rows: 2 kernels per batch of <= 2^28 rows
-    launches_per_step = 2 * ((rows + (1 << 28) - 1) >> 28) if rows >= (1 << 22) else 1
+    # count(*) on a 1027^2 grid takes the ring-partition path from 2^22 rows: 2 kernels (+ 2 memsets) per batch of <= 2^30 rows
+    ring = rows >= (1 << 22)
+    nbatch = (rows + (1 << 30) - 1) >> 30
+    launches_per_step = 2 * nbatch if ring else 1
     peak, peak_src = measured_peak()
     achieved = BYTES_PER_ROW * rows / (kms * 1e-3) / 1e9
+    # DRAM traffic of the timed build, from the kernels' own counters (b200_ctx_path_stats): every row's keys are read once
+    # (8 B), every 16-bit scratch entry is written once by k_ring_partition and read once by k_ring_count, plus the list tables
+    # that are memset before the pass; the grid (8.4 MB) stays in the L2.  profiles/r02_ncu_ring_v5.txt has the profiler's view of
+    # the same pair (dram__bytes 12.0 B/row).
+    st = ctx.path_stats(0) if ring else None
+    traffic = None
+    if st and st["rows"]:
+        per_batch = st["rows"] * BYTES_PER_ROW + st["entries"] * 2 * 2 + st["memset_bytes"]
+        traffic = per_batch * rows / st["rows"] / 1e9
 
     out = {
         "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"df.count(binby=[x,y], limits=[[-3,3]]*2, shape=1024) on {rows:.3g} fp32 rows per GPU, device-resident columns",
+        "config": {"workload": f"df.count(binby=[x,y], limits=[[-3,3]]*2, shape=1024) on {rows:.4g} fp32 rows per GPU, device-resident columns"
+                               + (" = BASELINE configs[4] (1e10 rows over 8 GPUs)" if world == 8 and rows == 1_250_000_000 else ""),
                    "rows_per_gpu": rows, "grid_cells": cells, "parallelism": f"row-shard x{world} + NCCL all-reduce of the int64 grid",
                    "l2": "inputs (8 GB/GPU) far exceed L2; no flush needed", "index_math": "fp64, bit-exact with the reference"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of the two kernels of one batch, `ncu --set full` capture
-                     # profiles/r01_ncu_final_tilecount_pair.txt: 3.391 GB per 2.6e8 rows = 13.04 B/row (8 algorithmic + 2 B/row of
-                     # bucket writes + 2 B/row of bucket reads + chunk padding), scaled to the rows of one step
-                     "traffic": (13.04 * rows / 1e9) if rows >= (1 << 22) else None, "traffic_unit": "GB per step",
-                     "peak_source": peak_src, "kernel": "k_tile_partition<float,2,TMA> + k_tile_count (csrc/tilecount.cu)" if rows >= (1 << 22) else "k_binby_fast",
+                     "traffic": traffic, "traffic_unit": "GB per step",
+                     "traffic_source": "counters of the timed build (b200_ctx_path_stats): 8 B/row keys + 2 x 2 B per scratch entry + memsets" if traffic else None,
+                     "scratch_entries_per_row": (st["entries"] / st["rows"]) if st and st["rows"] else None,
+                     "peak_source": peak_src, "kernel": "k_ring_partition<float,2> + k_ring_count (csrc/ringcount.cu)" if ring else "k_binby_fast",
                      "kernel_ms": kms, "algorithmic_bytes_per_row": BYTES_PER_ROW, "launches_per_step": launches_per_step,
                      "note": "achieved = 8 B/row x rows per step / device time of the step's binby launches (CUDA events on the launching "
-                             "stream); bound by SM instruction issue in k_tile_partition, not by HBM: see DESIGN.md section 4 and profiles/"},
+                             "stream); both kernels are bound by shared-memory atomic throughput (one ATOMS per row each), see DESIGN.md section 4"},
         "gpu_launches": args.steps * launches_per_step,
         "clocks": clocks,
     }
 
-    # ---- BASELINE.json configs[1] (df.sum(z, binby=[x,y], shape=1024) on the same rows), reported beside the headline -----
-    if rank == 0 and world == 1 and not args.no_cpu:
-        z = torch.empty(rows, dtype=torch.float32, device="cuda").normal_(generator=gen)
-        asum = superagg.AggSum_float32(grid, 1, 4)
-        asum.set_data(0, z, 0)
-
-        def sum_step():
-            asum.reset(0)
-            grid.bin(0, [asum], rows)
-        sum_step()
-        torch.cuda.synchronize()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record(stream)
-        for _ in range(3):
-            sum_step()
-        s1.record(stream)
-        ctx.sync(0)
-        torch.cuda.synchronize()
-        sms = s0.elapsed_time(s1) / 3
-        out["also"] = {"configs[1] df.sum(z, binby=[x,y], shape=1024), fp32, device-resident": {
-            "rows_per_s": rows / (sms * 1e-3), "ms_per_step": sms, "algorithmic_bytes_per_row": 12,
-            "achieved_gbs": 12 * rows / (sms * 1e-3) / 1e9, "frac": 12 * rows / (sms * 1e-3) / 1e9 / peak,
-            "kernel": "k_binby_fast<float,2,float> (one RED.ADD.F64 per row: L2-request bound, DESIGN.md section 4)"}}
-        del z, asum
-
-    # ---- e2e: host buffers through the C ABI, H2D inside the timed region -------------------------------------------
+    # ---- e2e: host buffers through the reference-facing task part, H2D inside the timed region ------------------------------
     if not args.no_e2e:
-        erows = int(args.e2e_rows)
-        chunk = int(args.e2e_chunk)
-        xh = torch.empty(erows, dtype=torch.float32).pin_memory()
-        yh = torch.empty(erows, dtype=torch.float32).pin_memory()
-        xh.copy_(x[:erows])
-        yh.copy_(y[:erows])
-        xn, yn = xh.numpy(), yh.numpy()
-        nslots = 4
-
-        def e2e_step():
-            agg.reset(0)
-            ctx.sync(0)
-            for c, i1 in enumerate(range(0, erows, chunk)):
-                i2 = min(i1 + chunk, erows)
-                s = c % nslots
-                bx.set_data(s, xn[i1:i2])
-                by.set_data(s, yn[i1:i2])
-                grid.bin(s, [agg], i2 - i1, row_offset=i1, flags=_lib.FLAG_ASYNC_HOST)
-            ctx.sync(-1)
-            if world > 1:
-                engine.all_reduce([agg], slot=0)
-            agg.read_async(0, host_grid)
-            ctx.sync(0)
-
-        e2e_step()
-        barrier()
-        sampler2 = ClockSampler(local)
-        sampler2.start()
-        w0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        barrier()
-        w = time.perf_counter() - w0
-        c2 = sampler2.result()
-        if c2.get("sm_mhz") is not None:  # the e2e steps are a timed region too: fold their clock samples in
-            both = sorted(sampler.samples + sampler2.samples)
-            out["clocks"] = {"sm_mhz": both[len(both) // 2], "sm_max_mhz": c2["sm_max_mhz"], "reasons": sorted(set(clocks["reasons"]) | set(c2["reasons"])),
-                             "samples": len(both), "windows": "device-resident steps + e2e steps"}
-        if world > 1:
-            t = torch.tensor([w], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            w = float(t.item())
-        assert int(host_grid.sum().item()) == erows * world
-        out["e2e"] = {"value": erows * world * args.e2e_steps / w, "unit": "rows/s", "h2d_bytes_per_step": erows * BYTES_PER_ROW,
-                      "d2h_bytes_per_step": cells * 8, "rows_per_step_per_gpu": erows, "chunk_rows": chunk, "slots": nslots,
-                      "note": "pinned host columns -> b200_bin(HOST, ASYNC) on 4 slots (H2D overlapped with kernels) -> grid D2H"}
-        # restore device-resident columns on slot 0
-        bx.set_data(0, x)
-        by.set_data(0, y)
+        out["e2e"] = e2e_leg(args, ctx, world, rank, local, x, y, barrier, sampler, out)
 
     # ---- CPU baseline (rank 0, N=1 only): the compiled reference on the host cores, bounded sample -------------------
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -373,6 +562,9 @@ def run_b200(args):
         for _ in range(3):
             cgrid, dt, kind, cores = cpu_reference_run(xc, yc, nthreads)
             best = dt if best is None else min(best, dt)
+        # the same code on ONE thread, on a smaller sample
+        r1 = min(crows, 20_000_000)
+        _, dt1, _, _ = cpu_reference_run(xc[:r1], yc[:r1], 1)
         # parity on the sample while we are here: the GPU grid for the same rows must be bit-identical
         agg.reset()
         bx.set_data(0, x[:crows])
@@ -381,7 +573,16 @@ def run_b200(args):
         ggrid = agg.get_result()
         out["cpu_baseline"] = {"value": crows / best, "unit": "rows/s", "cores": cores, "kind": kind, "host_cpus": os.cpu_count(),
                                "sample": f"first {crows} rows of the GPU arrays, best of 3, executor chunk loop restated (1M-row chunks), includes get_result fold",
+                               "one_thread": {"value": r1 / dt1, "unit": "rows/s", "cores": 1, "sample": f"first {r1} rows"},
                                "parity_on_sample": bool(np.array_equal(np.asarray(cgrid), ggrid))}
+        out["config"]["cpu_baseline_sample_rows"] = crows
+        del xc, yc
+
+    # ---- the other BASELINE.json configurations at full size, each with a parity check against the compiled reference --------
+    if rank == 0 and world == 1 and not args.no_also:
+        del x, y, bx, by, grid, agg
+        torch.cuda.empty_cache()
+        out["also"] = also_configs(args, ctx, stream, gen, peak, rows, os.cpu_count() or 1)
 
     if rank == 0:
         print(json.dumps(out), flush=True)

@@ -83,7 +83,11 @@ typedef enum {
 typedef enum { B200_MEM_HOST = 0, B200_MEM_DEVICE = 1, B200_MEM_MIXED = 2 } b200_memspace;
 
 /* flags for b200_bin / b200_set_update */
-#define B200_FLAG_ASYNC_HOST 1u /* host buffers stay valid until b200_ctx_sync(slot): do not wait for the H2D copies */
+/* Host chunks (B200_MEM_HOST) are by default memcpy'd into the slot's page-locked bounce ring inside the call: the caller's buffers
+ * are only read during the call (vaex/cpu.py:708-710) and the call returns without waiting for the device.  With
+ * B200_FLAG_ASYNC_HOST the copies are issued straight from the caller's buffers, which must then stay valid (and should be
+ * page-locked, b200_host_register) until b200_ctx_sync(slot). */
+#define B200_FLAG_ASYNC_HOST 1u
 
 typedef struct b200_ctx b200_ctx;
 typedef struct b200_agg b200_agg;

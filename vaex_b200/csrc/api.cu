@@ -72,6 +72,39 @@ int Stager::commit() {
         need += align_up(e.bytes, 256);
     B200_CHECK(slot_reserve(ctx, slot, need));
     size_t off = 0;
+    // MIXED keeps per-column copies (some columns are device pointers and were not planned); HOST chunks whose buffers die with
+    // the call go through the slot's page-locked bounce ring
+    const bool bounce = !async_host && memspace == B200_MEM_HOST;
+    char *pin = nullptr;
+    if (bounce) {
+        const unsigned b = slot->bounce_next++ & 1u;
+        if (!slot->bounce_done[b])
+            B200_CUDA(cudaEventCreateWithFlags(&slot->bounce_done[b], cudaEventDisableTiming));
+        B200_CUDA(cudaEventSynchronize(slot->bounce_done[b])); // the copy that last read this buffer has finished
+        if (slot->bounce_cap[b] < need) {
+            if (slot->bounce[b])
+                B200_CUDA(cudaFreeHost(slot->bounce[b]));
+            slot->bounce[b] = nullptr;
+            slot->bounce_cap[b] = 0;
+            const size_t cap = align_up(need + need / 4, 1 << 20);
+            B200_CUDA(cudaHostAlloc(&slot->bounce[b], cap, cudaHostAllocPortable));
+            slot->bounce_cap[b] = cap;
+        }
+        pin = static_cast<char *>(slot->bounce[b]);
+        // pieces of 4 MB: the asynchronous copy of one piece runs while this thread memcpy's the next one
+        constexpr size_t kPiece = 4u << 20;
+        for (auto &e : entries) {
+            e.dev = static_cast<char *>(slot->stage) + off;
+            for (size_t q = 0; q < e.bytes; q += kPiece) {
+                const size_t len = std::min(kPiece, e.bytes - q);
+                memcpy(pin + off + q, static_cast<const char *>(e.host) + q, len);
+                B200_CUDA(cudaMemcpyAsync(static_cast<char *>(e.dev) + q, pin + off + q, len, cudaMemcpyHostToDevice, slot->stream));
+            }
+            off += align_up(e.bytes, 256);
+        }
+        B200_CUDA(cudaEventRecord(slot->bounce_done[b], slot->stream));
+        return B200_OK;
+    }
     for (auto &e : entries) {
         e.dev = static_cast<char *>(slot->stage) + off;
         off += align_up(e.bytes, 256);
@@ -239,6 +272,12 @@ int b200_ctx_destroy(b200_ctx *ctx) {
         cudaFree(s->scratch);
         cudaFree(s->dscratch);
         cudaFreeHost(s->pinned);
+        for (int b = 0; b < 2; b++) {
+            if (s->bounce[b])
+                cudaFreeHost(s->bounce[b]);
+            if (s->bounce_done[b])
+                cudaEventDestroy(s->bounce_done[b]);
+        }
         cudaEventDestroy(s->h2d_done);
         cudaStreamDestroy(s->stream);
         delete s;
@@ -756,6 +795,7 @@ int b200_bin(b200_ctx *ctx, int slot, const b200_binner *binners, int nbinners, 
 
     // stage host columns (each distinct pointer once)
     Stager stg{ctx, sl, memspace};
+    stg.async_host = (flags & B200_FLAG_ASYNC_HOST) != 0;
     for (int i = 0; i < nbinners; i++) {
         stg.plan(binners[i].data, (size_t)nrows * db[i].isz);
         if (binners[i].mask)
@@ -877,9 +917,10 @@ int b200_bin(b200_ctx *ctx, int slot, const b200_binner *binners, int nbinners, 
     }
     B200_CHECK(flush());
 
-    if (memspace != B200_MEM_DEVICE && !(flags & B200_FLAG_ASYNC_HOST)) {
-        // the caller's buffers are only valid during the call (vaex/cpu.py:708-710).  Callers that keep them alive pass
-        // B200_FLAG_ASYNC_HOST and overlap the next chunk's H2D copy (another slot) with this slot's kernel.
+    if (memspace == B200_MEM_MIXED && !(flags & B200_FLAG_ASYNC_HOST)) {
+        // MIXED copies straight from the caller's host buffers, which are only valid during the call (vaex/cpu.py:708-710).
+        // Plain HOST chunks were memcpy'd into the slot's page-locked bounce ring: nothing of the caller's is read after return,
+        // so there is no wait here and the next chunk (another slot, or this one) overlaps this chunk's copy and kernels.
         B200_CUDA(cudaStreamSynchronize(st));
     }
     return B200_OK;

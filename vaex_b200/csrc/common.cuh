@@ -74,6 +74,13 @@ struct Slot {
     void *stage = nullptr; // device staging arena for host chunks
     size_t stage_cap = 0;
     void *pinned = nullptr; // small pinned scratch (results of reductions)
+    // host-chunk ingestion: two page-locked bounce buffers; a host column is memcpy'd into one of them by the calling thread and
+    // travels to the arena with ONE asynchronous copy, so the call returns without waiting for the device (the caller's buffer
+    // is only valid during the call, vaex/cpu.py:708-710)
+    void *bounce[2] = {nullptr, nullptr};
+    size_t bounce_cap[2] = {0, 0};
+    cudaEvent_t bounce_done[2] = {nullptr, nullptr};
+    unsigned bounce_next = 0;
     void *dscratch = nullptr;
     void *scratch = nullptr; // partition scratch (ringcount pool + list tables, tilesort buckets)
     size_t scratch_cap = 0;
@@ -122,6 +129,7 @@ struct Stager {
     b200_ctx *ctx;
     Slot *slot;
     int memspace;
+    bool async_host = false; // the caller keeps its host buffers alive until b200_ctx_sync(slot): copy straight from them
     size_t used = 0;
     struct Entry {
         const void *host;

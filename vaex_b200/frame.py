@@ -157,14 +157,21 @@ class Frame:
         """df.nunique (vaex/dataframe.py nunique -> agg.nunique -> AggNUnique_<dtype>, src/agg_nunique.cpp)."""
         return self._agg(_agg.nunique(expression, dropna=dropna, dropnan=dropnan, dropmissing=dropmissing), binby, limits, shape, selection, edges)
 
-    def _as_float64(self, expression):
-        """var/std/skew/kurtosis run on ``expression.astype('float64')`` in the reference (vaex/agg.py:429-431)."""
-        col = self.columns[expression]
-        if _dtype_of(col) == np.float64 or _dtype_of(col).kind == "f":
+    def _as_float64(self, expression, columns=None):
+        """var/std/skew/kurtosis run on ``expression.astype('float64')`` in the reference (vaex/agg.py:429-431, 466, 493): integer
+        columns must not accumulate their powers in int64 grids.  The cast keeps the mask of a masked column (numpy's astype
+        does), so masked rows stay out of count / sum / sum_moment."""
+        columns = self.columns if columns is None else columns
+        col = columns[expression]
+        if _dtype_of(col).kind == "f":
             return expression  # float32 already accumulates in double: identical result without the cast
         name = f"astype({expression}, 'float64')"
-        if name not in self.columns:
-            self.columns[name] = col.double() if _is_device(col) else np.asarray(col).astype("float64")
+        if _is_device(col):
+            columns[name] = col.double()
+        elif np.ma.isMaskedArray(col):
+            columns[name] = np.ma.array(np.asarray(col.data).astype("float64"), mask=np.ma.getmaskarray(col))
+        else:
+            columns[name] = np.asarray(col).astype("float64")
         return name
 
     # ---- value_counts / unique (counter<T>, SURVEY.md 8f row 3) ----------------------------------------------------------
@@ -268,10 +275,13 @@ class GroupBy:
         """actions: {column: [names]} | {column: name} | [descriptors]; returns dict of arrays (one row per non-empty group)."""
         df = self.df
         descs, labels = [], []
+        columns = dict(df.columns)
         if isinstance(actions, dict):
             for col, names in actions.items():
                 for n in ([names] if isinstance(names, str) else names):
-                    descs.append(_agg.aggregates[n](col))
+                    # the moment aggregators take expression.astype('float64') like Frame.var/std do (vaex/agg.py:429-431)
+                    src = df._as_float64(col, columns) if n in ("var", "std", "skew", "kurtosis") else col
+                    descs.append(_agg.aggregates[n](src))
                     labels.append(f"{col}_{n}")
         else:
             for d in actions:
@@ -279,7 +289,6 @@ class GroupBy:
                 labels.append(f"{d.expressions[0] if d.expressions else 'count'}_{d.short_name}")
         descs.append(_agg.count("*"))  # the reference adds count(*) to drop empty groups (vaex/groupby.py:688-745)
         labels.append("__count")
-        columns = dict(df.columns)
         specs = []
         if self.combined is not None:
             codes, chm = self.combined
