@@ -33,7 +33,11 @@ struct b200_set {
     b200::SetSlot *probe = nullptr; // first = global ordinal
     uint64_t probe_cap = 0;
     long long *d_offsets = nullptr; // nmaps
-    std::vector<uint64_t> h_keys;   // canonical patterns in ordinal order (special slots hold 0)
+    std::vector<uint64_t> h_keys;   // canonical patterns in ordinal order (special slots hold 0); filled lazily from d_keys_ord
+    bool h_keys_valid = false;
+    unsigned long long *d_keys_ord = nullptr; // n_entries canonical patterns in ordinal order (device)
+    uint64_t n_entries = 0;                   // keys + NaN + null slots
+    int64_t max_call_rows = 0;                // largest update so far: bounds the row part of every tag
     std::vector<int64_t> h_offsets;
     int64_t n_keys = 0, nan_count = 0, null_count = 0;
     int64_t nan_value = 0x7fffffff, null_value = 0x7fffffff; // src/hash_primitives.hpp:447
@@ -48,12 +52,6 @@ enum { CTR_COUNT = 0, CTR_OVERFLOW, CTR_NAN_COUNT, CTR_NULL_COUNT, CTR_NAN_TAG, 
 namespace {
 
 constexpr unsigned long long kTagLowMask = (1ULL << 40) - 1;
-
-struct Entry {
-    unsigned long long hi;  // shard
-    unsigned long long tag; // first occurrence
-    unsigned long long key;
-};
 
 __device__ __forceinline__ uint64_t load_raw1(const void *data, int isz, long long i) {
     switch (isz) {
@@ -72,14 +70,19 @@ constexpr int kMaxProbe = 96;
 __device__ __forceinline__ bool table_insert(SetSlot *table, unsigned long long mask, unsigned long long canon, unsigned long long tag) {
     unsigned long long h = hash64(canon) & mask;
     for (int step = 0; step < kMaxProbe; step++) {
-        unsigned long long k = table[h].key;
+        // ONE 16-byte L2 load per probe: key and tag share a sector.  A stale tag is harmless: tags only decrease, so at worst the
+        // atomicMin below is issued although it changes nothing
+        const ulonglong2 slot = __ldcg(reinterpret_cast<const ulonglong2 *>(table + h));
+        unsigned long long k = slot.x;
+        unsigned long long first = slot.y;
         if (k == SET_EMPTY) {
             k = atomicCAS(&table[h].key, SET_EMPTY, canon);
             if (k == SET_EMPTY)
                 k = canon;
+            first = ~0ull;
         }
         if (k == canon) {
-            if (tag < *reinterpret_cast<volatile unsigned long long *>(&table[h].first))
+            if (tag < first)
                 atomicMin(&table[h].first, tag);
             return true;
         }
@@ -162,8 +165,10 @@ __global__ void __launch_bounds__(256) k_set_count(const SetSlot *table, unsigne
             n_sent += w;
             continue;
         }
+        // the key is present (the insert pass of these rows succeeded); a rehash may have placed it further than kMaxProbe from its
+        // home slot, so the probe is bounded by the empty slot only
         unsigned long long h = hash64(canon) & mask;
-        for (int step = 0; step < kMaxProbe; step++) {
+        while (true) {
             const unsigned long long k = table[h].key;
             if (k == canon) {
                 atomicAdd(counts + h, w);
@@ -214,11 +219,13 @@ __global__ void k_set_rehash(const SetSlot *old, unsigned long long old_cap, Set
     }
 }
 
-__global__ void k_set_compact(const SetSlot *table, unsigned long long cap, unsigned long long *ctr, Entry *out, int dtype, int nmaps) {
+// occupied slots -> dense arrays (unordered): sort key = first-occurrence tag, payload = shard << 32 | index into ckey
+__global__ void k_set_compact(const SetSlot *table, unsigned long long cap, unsigned long long *ctr, unsigned long long *ckey, unsigned long long *ctag,
+                              unsigned long long *cval, int dtype, int nmaps) {
     const unsigned lane = threadIdx.x & 31;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long k = table[i].key;
-        const bool occ = k != SET_EMPTY;
+        const ulonglong2 slot = *reinterpret_cast<const ulonglong2 *>(table + i);
+        const bool occ = slot.x != SET_EMPTY;
         // one cursor bump per warp, not per occupied slot (same-address atomics serialise in the L2)
         const unsigned act = __activemask();
         const unsigned m = __ballot_sync(act, occ);
@@ -227,49 +234,147 @@ __global__ void k_set_compact(const SetSlot *table, unsigned long long cap, unsi
         if (occ && (int)lane == leader)
             base = atomicAdd(ctr + CTR_CURSOR, (unsigned long long)__popc(m));
         base = __shfl_sync(act, base, leader < 0 ? 0 : leader);
-        if (occ && out) { // out == nullptr: counting pass only
+        if (occ && ckey) { // ckey == nullptr: counting pass only
             const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
-            out[pos].hi = key_hash(dtype, k) % (unsigned long long)nmaps;
-            out[pos].tag = table[i].first;
-            out[pos].key = k;
+            ckey[pos] = slot.x;
+            ctag[pos] = slot.y;
+            cval[pos] = ((key_hash(dtype, slot.x) % (unsigned long long)nmaps) << 32) | pos;
         }
     }
 }
 
-__global__ void k_fill_entries(Entry *e, unsigned long long from, unsigned long long to) {
-    for (unsigned long long i = from + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < to; i += (unsigned long long)gridDim.x * blockDim.x) {
-        e[i].hi = 0xFFFFFFFFFFFFFFFFULL;
-        e[i].tag = 0xFFFFFFFFFFFFFFFFULL;
-        e[i].key = 0;
+// ---- LSD radix sort of (64-bit sort key, 64-bit payload) pairs, 8 bits per pass, stable --------------------------------------
+// Replaces round 1's bitonic network (210 launches for 2^20 entries) + a 24 MB download + a host loop.  One pass = per-block digit
+// histograms (digit-major), one exclusive scan over the 256 x nblocks matrix, a stable scatter.  `from_val`: the digit comes from
+// the payload's upper word (the shard) instead of the key.
+constexpr int kRadixThreads = 256;
+
+__global__ void __launch_bounds__(kRadixThreads) k_radix_hist(const unsigned long long *key, const unsigned long long *val, unsigned long long n, int shift,
+                                                              int from_val, unsigned *hist, unsigned nblk) {
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long i = (unsigned long long)blockIdx.x * kRadixThreads + threadIdx.x;
+    if (i < n) {
+        const unsigned long long x = from_val ? (val[i] >> 32) : key[i];
+        atomicAdd(&h[(x >> shift) & 255u], 1u);
     }
+    __syncthreads();
+    hist[(unsigned long long)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
 }
 
-// one compare-exchange stage of a bitonic sort on (hi, tag)
-__global__ void k_bitonic(Entry *e, unsigned long long n, unsigned long long j, unsigned long long k) {
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        unsigned long long l = i ^ j;
-        if (l > i) {
-            Entry a = e[i], b = e[l];
-            const bool a_gt_b = a.hi > b.hi || (a.hi == b.hi && a.tag > b.tag);
-            const bool a_lt_b = a.hi < b.hi || (a.hi == b.hi && a.tag < b.tag);
-            const bool up = (i & k) == 0;
-            if (up ? a_gt_b : a_lt_b) {
-                e[i] = b;
-                e[l] = a;
+// exclusive scan of `n` counters in place (single CTA of 1024 threads: n is 256 x nblocks <= a few million)
+__global__ void __launch_bounds__(1024) k_scan_u32(unsigned *a, unsigned long long n) {
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0)
+        carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned long long base = 0; base < n; base += 1024) {
+        const unsigned long long i = base + threadIdx.x;
+        const unsigned v = i < n ? a[i] : 0u;
+        unsigned x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o)
+                x += y;
+        }
+        if (lane == 31)
+            warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o)
+                    w += y;
             }
+            warp_sums[lane] = w;
         }
+        __syncthreads();
+        const unsigned before = carry + (warp ? warp_sums[warp - 1] : 0u) + x - v;
+        if (i < n)
+            a[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023)
+            carry = before + v;
+        __syncthreads();
     }
 }
 
-__global__ void k_probe_build(SetSlot *probe, unsigned long long mask, const Entry *e, unsigned long long n, unsigned long long skip0, unsigned long long skip1,
-                              unsigned long long skip2) {
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        if (i == skip0 || i == skip1 || i == skip2)
-            continue; // NaN / null / sentinel-key positions
-        unsigned long long k = e[i].key;
-        unsigned long long h = hash64(k) & mask;
+__global__ void __launch_bounds__(kRadixThreads) k_radix_scatter(const unsigned long long *key, const unsigned long long *val, unsigned long long *key_out,
+                                                                 unsigned long long *val_out, unsigned long long n, int shift, int from_val,
+                                                                 const unsigned *hist, unsigned nblk) {
+    __shared__ unsigned wcnt[kRadixThreads / 32][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int w = 0; w < kRadixThreads / 32; w++)
+        wcnt[w][threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long i = (unsigned long long)blockIdx.x * kRadixThreads + threadIdx.x;
+    const bool live = i < n;
+    unsigned long long k = 0, v = 0;
+    unsigned d = 0;
+    if (live) {
+        k = key[i];
+        v = val[i];
+        d = (unsigned)(((from_val ? (v >> 32) : k) >> shift) & 255u);
+    }
+    const unsigned act = __ballot_sync(0xffffffffu, live);
+    unsigned lrank = 0;
+    if (live) {
+        const unsigned m = __match_any_sync(act, d);
+        lrank = __popc(m & ((1u << lane) - 1u));
+        if (lrank == 0)
+            wcnt[warp][d] = __popc(m);
+    }
+    __syncthreads();
+    { // exclusive prefix over the warps, per digit (thread t owns digit t)
+        unsigned run = 0;
+        for (int w = 0; w < kRadixThreads / 32; w++) {
+            const unsigned t = wcnt[w][threadIdx.x];
+            wcnt[w][threadIdx.x] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    if (live) {
+        const unsigned long long pos = (unsigned long long)hist[(unsigned long long)d * nblk + blockIdx.x] + wcnt[warp][d] + lrank;
+        key_out[pos] = k;
+        val_out[pos] = v;
+    }
+}
+
+// after the sort: position == global ordinal.  Gathers the keys into ordinal order, builds the {key, ordinal} probe table, notes
+// where every shard starts and where the special entries (indices >= n_table of the compacted arrays) ended up.
+__global__ void k_set_finish(const unsigned long long *val, const unsigned long long *ckey, unsigned long long E, unsigned long long n_table, int sent_idx,
+                             int nan_idx, int null_idx, SetSlot *probe, unsigned long long pmask, unsigned long long *keys_ord, long long *shard_first,
+                             long long *special_ord) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long v = val[i];
+        const unsigned shard = (unsigned)(v >> 32);
+        const unsigned long long src = v & 0xffffffffull;
+        if (i == 0 || (unsigned)(val[i - 1] >> 32) != shard)
+            shard_first[shard] = (long long)i;
+        unsigned long long k = ckey[src];
+        if (src >= n_table) {
+            const int which = (int)(src - n_table);
+            if (which == sent_idx) {
+                special_ord[0] = (long long)i;
+            } else {
+                special_ord[which == nan_idx ? 1 : 2] = (long long)i;
+                keys_ord[i] = 0;
+                continue; // NaN / null: not a key of the probe table
+            }
+            keys_ord[i] = k;
+            continue; // the key whose pattern equals SET_EMPTY cannot live in the table either
+        }
+        keys_ord[i] = k;
+        unsigned long long h = hash64(k) & pmask;
         while (atomicCAS(&probe[h].key, SET_EMPTY, k) != SET_EMPTY)
-            h = (h + 1) & mask;
+            h = (h + 1) & pmask;
         probe[h].first = i;
     }
 }
@@ -393,7 +498,10 @@ int read_ctr(b200_set *s, cudaStream_t st, unsigned long long *h) {
     return B200_OK;
 }
 
-// lazily materialise ordinals; caller holds s->mu
+// lazily materialise ordinals; caller holds s->mu.  Everything stays on the device: compact -> radix sort by first-occurrence tag
+// (only the bytes that vary) -> stable radix pass(es) by shard -> position == global ordinal (src/hash.hpp:337-353) -> keys in
+// ordinal order + {key, ordinal} probe table.  The host learns nmaps shard starts and three special ordinals; key_array() copies
+// the ordered keys on demand (ensure_host_keys).
 int set_finalize(b200_set *s) {
     if (!s->dirty)
         return B200_OK;
@@ -403,88 +511,143 @@ int set_finalize(b200_set *s) {
     unsigned long long zero = 0;
     // the insert kernel keeps no fill counter (see table_insert): count the occupied slots first, then compact them
     B200_CUDA(cudaMemcpyAsync(s->d_ctr + CTR_CURSOR, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
-    k_set_compact<<<nblocks(s->cap), 256, 0, st>>>(s->table, s->cap, s->d_ctr, nullptr, s->dtype, s->nmaps);
+    k_set_compact<<<nblocks(s->cap), 256, 0, st>>>(s->table, s->cap, s->d_ctr, nullptr, nullptr, nullptr, s->dtype, s->nmaps);
     B200_CHECK(read_ctr(s, st, h));
     h[CTR_COUNT] = h[CTR_CURSOR];
     B200_CUDA(cudaMemcpyAsync(s->d_ctr + CTR_CURSOR, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
     const bool has_nan = h[CTR_NAN_COUNT] > 0, has_null = h[CTR_NULL_COUNT] > 0, has_sent = h[CTR_SENTINEL_TAG] != 0xFFFFFFFFFFFFFFFFULL;
     const unsigned long long n_table = h[CTR_COUNT];
     const unsigned long long E = n_table + has_nan + has_null + has_sent;
-    unsigned long long P = 1;
-    while (P < E)
-        P <<= 1;
-    Entry *d_e = nullptr;
-    B200_CUDA(cudaMalloc(&d_e, sizeof(Entry) * (P ? P : 1)));
+    if (E >= (1ull << 32)) {
+        set_error("ordered_set: more than 2^32 distinct keys are not supported");
+        return B200_ERR_UNSUPPORTED;
+    }
+    // one allocation: ckey | tag A | val A | tag B | val B | radix histograms | shard starts | special ordinals
+    const unsigned nblk = (unsigned)((E + kRadixThreads - 1) / kRadixThreads);
+    const size_t en = (size_t)(E ? E : 1);
+    const size_t off_hist = 5 * en * 8, off_first = off_hist + align_up((size_t)256 * (nblk ? nblk : 1) * 4, 256), off_spec = off_first + align_up((size_t)s->nmaps * 8, 256);
+    char *work = nullptr;
+    B200_CUDA(cudaMalloc(&work, off_spec + 256));
+    unsigned long long *ckey = reinterpret_cast<unsigned long long *>(work), *tagA = ckey + en, *valA = tagA + en, *tagB = valA + en, *valB = tagB + en;
+    unsigned *hist = reinterpret_cast<unsigned *>(work + off_hist);
+    long long *d_first = reinterpret_cast<long long *>(work + off_first), *d_spec = reinterpret_cast<long long *>(work + off_spec);
     if (n_table)
-        k_set_compact<<<nblocks(s->cap), 256, 0, st>>>(s->table, s->cap, s->d_ctr, d_e, s->dtype, s->nmaps);
-    Entry extra[3];
-    int ne = 0;
-    if (has_sent)
-        extra[ne++] = Entry{key_hash(s->dtype, SET_EMPTY) % (unsigned long long)s->nmaps, h[CTR_SENTINEL_TAG], SET_EMPTY};
-    if (has_nan)
-        extra[ne++] = Entry{0, h[CTR_NAN_TAG], 0};
-    if (has_null)
-        extra[ne++] = Entry{0, h[CTR_NULL_TAG], 0};
-    if (ne)
-        B200_CUDA(cudaMemcpyAsync(d_e + n_table, extra, sizeof(Entry) * ne, cudaMemcpyHostToDevice, st));
-    if (P > E)
-        k_fill_entries<<<nblocks(P - E), 256, 0, st>>>(d_e, E, P);
-    for (unsigned long long k = 2; k <= P; k <<= 1)
-        for (unsigned long long j = k >> 1; j > 0; j >>= 1)
-            k_bitonic<<<nblocks(P), 256, 0, st>>>(d_e, P, j, k);
-    B200_CUDA(cudaGetLastError());
-    std::vector<Entry> he(E);
-    if (E)
-        B200_CUDA(cudaMemcpyAsync(he.data(), d_e, sizeof(Entry) * E, cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaStreamSynchronize(st));
-
-    s->h_keys.assign(E, 0);
-    s->h_offsets.assign(s->nmaps, 0);
-    s->nan_count = (int64_t)h[CTR_NAN_COUNT];
-    s->null_count = (int64_t)h[CTR_NULL_COUNT];
-    s->nan_value = s->null_value = 0x7fffffff;
-    s->sentinel_ordinal = -1;
-    s->n_keys = (int64_t)(n_table + has_sent);
-    std::vector<int64_t> per_shard(s->nmaps, 0);
-    // NaN and null carry distinct tags unless created by from_keys with equal rows (impossible: distinct rows)
-    for (unsigned long long i = 0; i < E; i++) {
-        const Entry &e = he[i];
-        per_shard[e.hi]++;
-        if (has_nan && e.hi == 0 && e.tag == h[CTR_NAN_TAG] && s->nan_value == 0x7fffffff && e.key == 0 && !(has_null && e.tag == h[CTR_NULL_TAG])) {
-            s->nan_value = (int64_t)i;
-        } else if (has_null && e.hi == 0 && e.tag == h[CTR_NULL_TAG] && s->null_value == 0x7fffffff && e.key == 0) {
-            s->null_value = (int64_t)i;
-        } else {
-            s->h_keys[i] = e.key;
-            if (e.key == SET_EMPTY)
-                s->sentinel_ordinal = (int64_t)i;
-        }
+        k_set_compact<<<nblocks(s->cap), 256, 0, st>>>(s->table, s->cap, s->d_ctr, ckey, tagA, valA, s->dtype, s->nmaps);
+    // the special entries ride along behind the table's keys: [key == SET_EMPTY pattern] [NaN] [null]; NaN / null live in shard 0
+    unsigned long long xk[3], xt[3], xv[3];
+    int ne = 0, sent_idx = -1, nan_idx = -1, null_idx = -1;
+    // NaN / null sort behind every row of the call that first saw them (row part kTagLowMask - 1 / kTagLowMask, see
+    // set_insert_device): keep that order but with a small row part, so that the sort can skip the empty high bytes
+    auto special_tag = [&](unsigned long long tag) {
+        const unsigned long long low = tag & kTagLowMask;
+        if (low < kTagLowMask - 1)
+            return tag; // from_keys: the tag is the row itself
+        return (tag & ~kTagLowMask) | ((unsigned long long)s->max_call_rows + (low - (kTagLowMask - 1)));
+    };
+    if (has_sent) {
+        sent_idx = ne;
+        xk[ne] = SET_EMPTY, xt[ne] = h[CTR_SENTINEL_TAG], xv[ne] = ((key_hash(s->dtype, SET_EMPTY) % (unsigned long long)s->nmaps) << 32) | (n_table + ne);
+        ne++;
     }
-    int64_t off = 0;
-    for (int m = 0; m < s->nmaps; m++) {
-        s->h_offsets[m] = off;
-        off += per_shard[m];
+    if (has_nan) {
+        nan_idx = ne;
+        xk[ne] = 0, xt[ne] = special_tag(h[CTR_NAN_TAG]), xv[ne] = n_table + ne;
+        ne++;
     }
-    // probe table
+    if (has_null) {
+        null_idx = ne;
+        xk[ne] = 0, xt[ne] = special_tag(h[CTR_NULL_TAG]), xv[ne] = n_table + ne;
+        ne++;
+    }
+    if (ne) {
+        B200_CUDA(cudaMemcpyAsync(ckey + n_table, xk, 8 * ne, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(tagA + n_table, xt, 8 * ne, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(valA + n_table, xv, 8 * ne, cudaMemcpyHostToDevice, st));
+    }
+    unsigned long long *tin = tagA, *vin = valA, *tout = tagB, *vout = valB;
+    auto pass = [&](int shift, int from_val) -> int {
+        k_radix_hist<<<nblk, kRadixThreads, 0, st>>>(tin, vin, E, shift, from_val, hist, nblk);
+        k_scan_u32<<<1, 1024, 0, st>>>(hist, 256ull * nblk);
+        k_radix_scatter<<<nblk, kRadixThreads, 0, st>>>(tin, vin, tout, vout, E, shift, from_val, hist, nblk);
+        B200_CUDA(cudaGetLastError());
+        std::swap(tin, tout);
+        std::swap(vin, vout);
+        return B200_OK;
+    };
+    if (E > 1) {
+        // tags are (call sequence << 40 | row): only the bytes that can differ are sorted on.  The NaN / null tags were moved just
+        // behind the largest row (see `special_tag`), so the row part stays below max_low.
+        const unsigned long long max_low = (unsigned long long)s->max_call_rows + 2, max_seq = (unsigned long long)(s->seq > 0 ? s->seq - 1 : 0);
+        for (int shift = 0; shift < 40 && (max_low >> shift); shift += 8)
+            B200_CHECK(pass(shift, 0));
+        for (int shift = 0; shift < 24 && (max_seq >> shift); shift += 8)
+            B200_CHECK(pass(40 + shift, 0));
+        for (int shift = 0; shift < 16 && ((unsigned)(s->nmaps - 1) >> shift); shift += 8)
+            B200_CHECK(pass(shift, 1));
+    }
+    // probe table + keys in ordinal order
     if (s->probe)
         B200_CUDA(cudaFree(s->probe));
+    s->probe = nullptr;
+    if (s->d_keys_ord)
+        B200_CUDA(cudaFree(s->d_keys_ord));
+    s->d_keys_ord = nullptr;
     uint64_t pc = 16;
     while (pc < 2 * (n_table + 1))
         pc <<= 1;
     B200_CUDA(cudaMalloc(&s->probe, pc * sizeof(SetSlot)));
     s->probe_cap = pc;
+    B200_CUDA(cudaMalloc(&s->d_keys_ord, en * 8));
     k_set_init<<<nblocks(pc), 256, 0, st>>>(s->probe, pc);
+    B200_CUDA(cudaMemsetAsync(d_first, 0xff, (size_t)s->nmaps * 8, st)); // -1: shard without keys
+    B200_CUDA(cudaMemsetAsync(d_spec, 0xff, 3 * 8, st));
     if (E)
-        k_probe_build<<<nblocks(E), 256, 0, st>>>(s->probe, pc - 1, d_e, E, has_nan ? (unsigned long long)s->nan_value : ~0ull,
-                                                  has_null ? (unsigned long long)s->null_value : ~0ull,
-                                                  has_sent ? (unsigned long long)s->sentinel_ordinal : ~0ull);
+        k_set_finish<<<nblocks(E), 256, 0, st>>>(vin, ckey, E, n_table, sent_idx, nan_idx, null_idx, s->probe, pc - 1, s->d_keys_ord, d_first, d_spec);
+    B200_CUDA(cudaGetLastError());
+    std::vector<long long> first(s->nmaps);
+    long long spec[3];
+    B200_CUDA(cudaMemcpyAsync(first.data(), d_first, (size_t)s->nmaps * 8, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(spec, d_spec, sizeof spec, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    B200_CUDA(cudaFree(work));
+
+    s->n_entries = E;
+    s->h_keys.clear();
+    s->h_keys_valid = false;
+    s->nan_count = (int64_t)h[CTR_NAN_COUNT];
+    s->null_count = (int64_t)h[CTR_NULL_COUNT];
+    s->nan_value = has_nan ? spec[1] : 0x7fffffff;
+    s->null_value = has_null ? spec[2] : 0x7fffffff;
+    s->sentinel_ordinal = has_sent ? spec[0] : -1;
+    s->n_keys = (int64_t)(n_table + has_sent);
+    // offsets[m] = where shard m starts; an empty shard starts where the next non-empty one does (src/hash.hpp:337-353)
+    s->h_offsets.assign(s->nmaps, 0);
+    long long next = (long long)E;
+    for (int m = s->nmaps - 1; m >= 0; m--) {
+        if (first[m] >= 0)
+            next = first[m];
+        s->h_offsets[m] = next;
+    }
     if (!s->d_offsets)
         B200_CUDA(cudaMalloc(&s->d_offsets, sizeof(long long) * s->nmaps));
     B200_CUDA(cudaMemcpyAsync(s->d_offsets, s->h_offsets.data(), sizeof(long long) * s->nmaps, cudaMemcpyHostToDevice, st));
-    B200_CUDA(cudaGetLastError());
     B200_CUDA(cudaStreamSynchronize(st));
-    B200_CUDA(cudaFree(d_e));
     s->dirty = false;
+    return B200_OK;
+}
+
+// key_array() / merge need the ordered keys on the host: one download per finalisation, on demand; caller holds s->mu
+int ensure_host_keys(b200_set *s) {
+    B200_CHECK(set_finalize(s));
+    if (s->h_keys_valid)
+        return B200_OK;
+    s->h_keys.assign(s->n_entries, 0);
+    if (s->n_entries) {
+        cudaStream_t st = s->ctx->slots[0]->stream;
+        B200_CUDA(cudaMemcpyAsync(s->h_keys.data(), s->d_keys_ord, s->n_entries * 8, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+    }
+    s->h_keys_valid = true;
     return B200_OK;
 }
 
@@ -502,6 +665,7 @@ int set_insert_device(b200_set *s, cudaStream_t st, const void *d_keys, const ui
     }
     const unsigned long long tag_base = from_keys ? 0ull : ((unsigned long long)s->seq << 40);
     s->seq++;
+    s->max_call_rows = std::max<int64_t>(s->max_call_rows, nrows);
     const unsigned long long first_low = kTagLowMask - 1, second_low = kTagLowMask;
     const unsigned long long null_low = use_offsets ? first_low : second_low;
     const unsigned long long nan_low = use_offsets ? second_low : first_low;
@@ -535,8 +699,12 @@ int set_insert_device(b200_set *s, cudaStream_t st, const void *d_keys, const ui
         redo = 0;
         row0 += n;
     }
-    if (s->counting && !s->hold_count_pass && !skip_keys && nrows)
+    if (s->counting && !s->hold_count_pass && !skip_keys && nrows) {
         k_set_count<<<nblocks((unsigned long long)nrows), 256, 0, st>>>(s->table, s->cap - 1, s->counts, s->d_ctr, s->dtype, isz, d_keys, d_masks, nullptr, nrows);
+        B200_CUDA(cudaGetLastError());
+        // finalisation, counts() and growth run on slot 0's stream: the counts must be complete before any of them looks
+        B200_CUDA(cudaStreamSynchronize(st));
+    }
     B200_CUDA(cudaGetLastError());
     s->dirty = true;
     return B200_OK;
@@ -609,7 +777,7 @@ int b200_set_counts(b200_set *s, int64_t *out) {
     std::lock_guard<std::mutex> g(s->mu);
     B200_CHECK(set_finalize(s));
     cudaStream_t st = s->ctx->slots[0]->stream;
-    const size_t n = s->h_keys.size();
+    const size_t n = (size_t)s->n_entries;
     if (!n)
         return B200_OK;
     unsigned long long *d_out = nullptr;
@@ -637,6 +805,7 @@ int b200_set_destroy(b200_set *s) {
     cudaFree(s->table);
     cudaFree(s->counts);
     cudaFree(s->probe);
+    cudaFree(s->d_keys_ord);
     cudaFree(s->d_ctr);
     cudaFree(s->d_offsets);
     delete s;
@@ -764,7 +933,7 @@ int b200_set_merge(b200_set *s, b200_set *const *others, int nothers) {
         }
         {
             std::lock_guard<std::mutex> g(o->mu);
-            B200_CHECK(set_finalize(o));
+            B200_CHECK(ensure_host_keys(o));
             keys.reserve(o->h_keys.size());
             for (size_t k = 0; k < o->h_keys.size(); k++)
                 if ((int64_t)k != o->nan_value && (int64_t)k != o->null_value) {
@@ -851,7 +1020,7 @@ int b200_set_offsets(b200_set *s, int64_t *out) {
 // hash_base::key_array (src/hash_primitives.hpp:302-328): NaN slot holds NaN, null slot holds (T)-1
 int b200_set_key_array(b200_set *s, void *out) {
     std::lock_guard<std::mutex> g(s->mu);
-    B200_CHECK(set_finalize(s));
+    B200_CHECK(ensure_host_keys(s));
     const int isz = dtype_size(s->dtype);
     for (size_t i = 0; i < s->h_keys.size(); i++) {
         uint64_t bits = s->h_keys[i];
