@@ -175,6 +175,7 @@ int64_t b200_set_null_count(b200_set *set);
 int64_t b200_set_nan_index(b200_set *set);
 int64_t b200_set_null_index(b200_set *set);
 int b200_set_nmaps(const b200_set *set);
+int b200_set_dtype(const b200_set *set);
 int b200_set_offsets(b200_set *set, int64_t *out /* nmaps */);
 int b200_set_key_array(b200_set *set, void *keys_out /* count * itemsize, host */);
 /* out dtype follows the reference: count < 2^7 -> I8, < 2^15 -> I16, < 2^31 -> I32, else I64 */
@@ -198,6 +199,43 @@ int b200_set_counts(b200_set *set, int64_t *counts_out);
 /* out[0] = min, out[1] = max over non-NaN, unmasked values, as double; out = {+inf,-inf} when empty.
  */
 int b200_minmax(b200_ctx *ctx, int slot, int dtype, int byteswap, const void *data, const uint8_t *mask, int64_t nrows, int memspace, double *out);
+
+/* ---- device-side expressions and filter compaction ------------------------------------------------
+ * Replaces the per-chunk Python `eval` of virtual columns / filters / selections (vaex/scopes.py:108-128 _BlockScope.evaluate) and
+ * the pre-filter compression of every dependent column (vaex/execution.py:516-522).  A program is the expression in postfix order;
+ * vaex_b200/expression.py builds it from the expression's AST and decides every node's numpy result type (so the results are
+ * bit-identical to numpy's).  `cls` is the class the operation computes in (for CAST / ORDINAL: the class of its operand). */
+typedef enum {
+    B200_EX_INPUT = 0, /* push inputs[arg][row] */
+    B200_EX_CONST_F64, /* push f (as float32 when cls == B200_EXC_F32) */
+    B200_EX_CONST_I64, /* push i */
+    B200_EX_ADD, B200_EX_SUB, B200_EX_MUL, B200_EX_DIV, /* one correctly rounded IEEE operation; integers wrap */
+    B200_EX_NEG, B200_EX_ABS, B200_EX_SQRT,
+    B200_EX_LT, B200_EX_LE, B200_EX_GT, B200_EX_GE, B200_EX_EQ, B200_EX_NE, /* -> bool */
+    B200_EX_AND, B200_EX_OR, B200_EX_NOT,                                   /* on bools */
+    B200_EX_CAST,   /* astype(b200_dtype arg) */
+    B200_EX_ORDINAL /* _ordinal_values(value, sets[arg]) -> int64 ordinal, -1 when absent (vaex/functions.py:2454-2463) */
+} b200_expr_opcode;
+typedef enum { B200_EXC_F64 = 0, B200_EXC_F32, B200_EXC_I64 /* any signed integer, sign-extended */, B200_EXC_U64, B200_EXC_BOOL } b200_expr_class;
+typedef struct {
+    int32_t op, cls, arg, reserved;
+    double f;
+    int64_t i;
+} b200_expr_op;
+typedef struct {
+    const void *data;
+    int32_t dtype; /* b200_dtype, native byte order */
+    int32_t reserved;
+} b200_expr_input;
+/* out_device: device buffer of nrows elements of out_dtype; the kernel is enqueued on the slot's stream (consume the result on the
+ * same slot).  <= 64 ops, 8 inputs, 4 sets, stack depth 12. */
+int b200_eval(b200_ctx *ctx, int slot, const b200_expr_op *prog, int nops, const b200_expr_input *inputs, int ninputs, b200_set *const *sets, int nsets,
+              int64_t nrows, int memspace, int out_dtype, void *out_device);
+/* stable compaction of up to 16 columns by a keep-mask (1 byte per row, non-zero = keep): outs_device[c] receives the kept rows of
+ * cols[c] in order; *count_out = rows kept (the call waits for it). */
+int b200_compact(b200_ctx *ctx, int slot, const uint8_t *keep, int ncols, const void *const *cols, const int32_t *dtypes, int64_t nrows, int memspace,
+                 void *const *outs_device, int64_t *count_out);
+
 
 /* ---- host-chunk ingestion ---------------------------------------------- */
 /* Page-lock a host column once (cudaHostRegister) so that the per-chunk H2D copies of b200_bin(HOST) run at PCIe rate and

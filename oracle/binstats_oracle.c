@@ -903,3 +903,37 @@ orc_set *orc_set_from_keys(int dtype, const void *keys, int64_t n, int64_t null_
     s->nan_count = nan_count;
     return s;
 }
+
+/* ---- limits pre-pass: df.minmax -> TaskStatistic(OP_MIN_MAX) -> vaexfast.statisticNd ---------------
+ * vaex/cpu.py:487-626 (TaskPartStatistic.process): rows masked in the column are dropped (:533-537); the column is cast with
+ * as_flat_array to float64 when its dtype is float64 or int64 and to FLOAT32 for every other dtype (:519-531 — int32 / uint64 / ...
+ * values are rounded to fp32 on the way, a quirk that is part of the observable result); byte-swapped input is read through
+ * functor_double_to_native (src/vaexfast.cpp:1339-1358).  The kernel op_min_max (src/vaexfast.cpp:1089-1101) starts from
+ * (+inf, -inf) (vaex/tasks.py StatOpMinMax.init) and keeps `value < min` / `value > max`: NaN never wins.
+ * out[0] = min, out[1] = max as doubles; DataFrame.minmax casts them back to the column dtype (vaex/dataframe.py:1524-1528),
+ * which the Python wrapper does. */
+int orc_minmax(int dtype, int flip, const void *data, const uint8_t *mask, uint64_t length, double out[2]) {
+    double lo = INFINITY, hi = -INFINITY;
+#define BODY(T)                                                                                                                \
+    for (uint64_t i = 0; i < length; i++) {                                                                                    \
+        if (mask && mask[i])                                                                                                   \
+            continue;                                                                                                          \
+        T v = ((const T *)data)[i];                                                                                            \
+        if (flip)                                                                                                              \
+            flip_bytes(&v, sizeof(T));                                                                                         \
+        double value;                                                                                                          \
+        if (dtype == ORC_F64 || dtype == ORC_I64)                                                                              \
+            value = (double)v; /* numpy astype(float64): round to nearest even */                                              \
+        else                                                                                                                   \
+            value = (double)(float)v; /* numpy astype(float32), then the kernel widens to double */                            \
+        if (value < lo)                                                                                                        \
+            lo = value;                                                                                                        \
+        if (value > hi)                                                                                                        \
+            hi = value;                                                                                                        \
+    }
+    FOR_DTYPE(dtype, BODY)
+#undef BODY
+    out[0] = lo;
+    out[1] = hi;
+    return 0;
+}

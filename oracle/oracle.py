@@ -88,6 +88,8 @@ def lib():
         L.orc_scalar_to_bins.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         L.orc_ordinal_to_bins.restype = C.c_int
         L.orc_ordinal_to_bins.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.orc_minmax.restype = C.c_int
+        L.orc_minmax.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -382,3 +384,25 @@ class OrderedSet:
 
     def flatten(self):
         return OrderedSet.from_keys(self.key_array(), self.null_index if self.has_null else -1, self.nan_count, self.null_count)
+
+
+# ------------------------------------------------------------------------------------------------
+# limits pre-pass (df.minmax): legacy TaskStatistic(OP_MIN_MAX) over vaexfast.statisticNd
+# ------------------------------------------------------------------------------------------------
+def minmax(data, raw=False):
+    """df.minmax(expression) for one column (numpy or numpy.ma array, any of the 11 dtypes, either byte order).
+    raw=True: the (min, max) doubles of the statistic grid; default: cast back to the column dtype like
+    vaex/dataframe.py:1524-1528 does (`value.astype(data_type0.numpy)`)."""
+    mask = None
+    if np.ma.isMaskedArray(data):
+        mask = np.ascontiguousarray(np.ma.getmaskarray(data)).view(np.uint8)
+        data = data.data
+    data = np.ascontiguousarray(data)
+    code, flip = dtype_code(data.dtype), int(is_swapped(data) and data.dtype.itemsize > 1)
+    out = np.empty(2, np.float64)
+    rc = lib().orc_minmax(code, flip, data.ctypes.data, None if mask is None else mask.ctypes.data, len(data), out.ctypes.data)
+    assert rc == 0
+    if raw:
+        return out
+    with np.errstate(invalid="ignore"):
+        return out.astype(data.dtype.newbyteorder("="))

@@ -252,3 +252,52 @@ def groupby_sum_count(keys, values, nthreads=1, nmaps=None):
         with ThreadPoolExecutor(nthreads) as pool:
             list(pool.map(work, ranges))
     return flat.key_array(), agg_sum.get_result(), agg_count.get_result()
+
+
+def vaexfast():
+    """the reference's legacy statistics module (src/vaexfast.cpp), compiled unmodified into oracle/_ref"""
+    import glob
+    if not glob.glob(os.path.join(_REF, "vaexfast*.so")):
+        raise RuntimeError("compiled vaexfast missing: run `make -C oracle ref` where /root/reference exists")
+    sys.path.insert(0, _REF)
+    try:
+        return importlib.import_module("vaexfast")
+    finally:
+        sys.path.remove(_REF)
+
+
+def minmax(data, raw=False, chunk=1024 * 1024):
+    """df.minmax(expression) restated around the compiled vaexfast.statisticNd: TaskPartStatistic.process (vaex/cpu.py:513-606:
+    masked rows dropped, dtype class -> statisticNd_f8 / _f4 via as_flat_array, non-native byte order handled inside), grid
+    initialised by StatOpMinMax.init, chunks of 1M rows, and the final astype to the column dtype (vaex/dataframe.py:1524-1528)."""
+    vf = vaexfast()
+    grid = np.zeros((2,), np.float64)
+    grid[0], grid[1] = np.inf, -np.inf
+    n = len(data)
+    for i1 in range(0, max(n, 1), chunk):
+        block = data[i1:i1 + chunk]
+        if np.ma.isMaskedArray(block):
+            block = np.asarray(block.data)[~np.ma.getmaskarray(block)]
+        block = np.asarray(block)
+        if len(block) == 0:  # the executor hands out no empty chunks; a fully masked chunk leaves nothing to reduce
+            continue
+        dtype = np.result_type(block.dtype)  # vaex/cpu.py:519-521: the NATIVE common dtype
+        if dtype.str in ">f8 <f8 =f8":
+            fn = vf.statisticNd_f8
+        elif dtype.str in ">f4 <f4 =f4":
+            fn = vf.statisticNd_f4
+        elif dtype.str in ">i8 <i8 =i8":
+            dtype, fn = np.dtype(np.float64), vf.statisticNd_f8
+        else:
+            dtype, fn = np.dtype(np.float32), vf.statisticNd_f4
+        # as_flat_array(block, dtype) (vaex/utils.py:691-695): float64 columns with an 8-byte stride pass through whatever their
+        # byte order (statisticNd then reads them through functor_double_to_native); everything else is astype'd to the native dtype
+        if block.dtype.type == dtype and block.strides[0] == 8:
+            flat = block
+        else:
+            flat = block.astype(dtype, copy=True)
+        fn([], [flat], grid, [], [], 2, 0)
+    if raw:
+        return grid
+    with np.errstate(invalid="ignore"):
+        return grid.astype(np.asarray(data).dtype.newbyteorder("="))

@@ -40,3 +40,20 @@ def binby_case(c):
             r = np.ma.array(r, mask=c[f"a{k}_result_mask"])
         expected.append(r)
     return binners, aggs, n, expected
+
+
+MINMAX_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "minmax_golden.npz")
+
+
+def load_minmax():
+    """tests/golden/minmax_golden.npz (tests/golden/make_golden_minmax.py): name -> (column incl. byte order / mask, raw (min, max)
+    doubles of the compiled reference's statistic grid, the pair cast back to the column dtype)."""
+    z = np.load(MINMAX_PATH, allow_pickle=False)
+    out = {}
+    for name in sorted({k.split("/")[0] for k in z.files}):
+        dt = np.dtype(str(z[name + "/dtype"]))
+        data = z[name + "/data"].view(dt) if dt.itemsize > 1 else z[name + "/data"]
+        if name + "/mask" in z.files:
+            data = np.ma.array(data, mask=z[name + "/mask"])
+        out[name] = (data, z[name + "/raw"], z[name + "/result"])
+    return out

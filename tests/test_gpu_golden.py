@@ -43,3 +43,28 @@ def test_hash64_golden():
     from vaex_b200 import superutils
     for i, o in zip(GOLD["hash64"]["in"], GOLD["hash64"]["out"]):
         assert superutils.hash(int(i)) == int(o)
+
+
+MINMAX = golden_util.load_minmax()
+
+
+@pytest.mark.parametrize("device", [False, True])
+@pytest.mark.parametrize("name", sorted(MINMAX))
+def test_minmax_matches_golden(name, device):
+    """Frame.minmax -> b200_minmax (csrc/minmax.cu) against the compiled reference's OP_MIN_MAX vectors: raw grid values and the
+    pair cast back to the column dtype, host chunks and device-resident columns."""
+    from helpers import to_device
+    from vaex_b200.frame import Frame
+    data, raw, result = MINMAX[name]
+    col = data
+    if device:
+        if np.ma.isMaskedArray(data) or (data.dtype.itemsize > 1 and data.dtype.byteorder not in ("=", "|", "<")):
+            pytest.skip("device columns are plain native arrays")
+        col = to_device(np.ascontiguousarray(data))
+        if data.dtype.kind == "u" and data.dtype.itemsize > 1:
+            pytest.skip("torch carries unsigned columns as signed views")
+    df = Frame({"v": col})
+    got_raw = df.minmax("v", raw=True)
+    assert np.array_equal(got_raw, raw, equal_nan=True), (name, got_raw, raw)
+    got = df.minmax("v")
+    assert got.dtype == result.dtype and np.array_equal(got, result, equal_nan=True)

@@ -283,3 +283,29 @@ def test_large_properties():
     inside = (x >= -3) & (x < 3)
     assert int(whole[2:-1, :].sum()) == int(inside.sum()) or abs(int(whole[2:-1, :].sum()) - int(inside.sum())) < 4
     del ix
+
+
+def test_minmax_large_unaligned_masked(oracle):
+    """the vectorised limits pre-pass at a size where every code path runs (scalar head, 4-deep vector body, tail; masks; a view
+    that starts off a 16-byte boundary), all dtypes, against the oracle"""
+    from helpers import to_device
+    from vaex_b200.frame import Frame
+    rng = np.random.default_rng(5)
+    n = (1 << 22) + 77
+    for dt in ("f8", "f4", "i8", "i4", "i2", "i1", "u1", "?"):
+        d = np.dtype(dt)
+        if d.kind == "f":
+            v = rng.standard_normal(n).astype(d)
+            v[::997] = np.nan
+        elif d.kind == "b":
+            v = rng.integers(0, 2, n).astype(d)
+        else:
+            info = np.iinfo(d)
+            v = rng.integers(info.min, info.max, n, dtype=np.int64, endpoint=True).astype(d)
+        for off in (0, 3):
+            w = v[off:]
+            want = oracle.minmax(w, raw=True)
+            assert np.array_equal(Frame({"v": w}).minmax("v", raw=True), want, equal_nan=True), (dt, off, "host")
+            assert np.array_equal(Frame({"v": to_device(v)[off:]}).minmax("v", raw=True), want, equal_nan=True), (dt, off, "device")
+        m = rng.random(n) < 0.5
+        assert np.array_equal(Frame({"v": np.ma.array(v, mask=m)}).minmax("v", raw=True), oracle.minmax(np.ma.array(v, mask=m), raw=True), equal_nan=True)

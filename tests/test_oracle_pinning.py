@@ -86,3 +86,43 @@ def test_reference_chunk_loop_is_thread_invariant_for_counts(nthreads, oracle, r
     want = oracle.binby(b, a, n)[0]
     got = ref.RefBinby(b, a, nthreads).run(n, chunk=50_000)[0]
     assert np.array_equal(want, np.asarray(got))
+
+
+# ---- limits pre-pass (df.minmax): SURVEY.md section 8f row 1 ------------------------------------------------------------------
+MINMAX = golden_util.load_minmax()
+
+
+@pytest.mark.parametrize("name", sorted(MINMAX))
+def test_oracle_minmax_matches_golden(name, oracle):
+    """oracle.minmax (orc_minmax) against vaexfast.statisticNd OP_MIN_MAX of the compiled reference: all 11 dtypes, masked,
+    byte-swapped, NaN / inf, integers beyond 2^24 / 2^53 (rounded by the reference's float casts), empty and all-NaN columns."""
+    data, raw, result = MINMAX[name]
+    assert np.array_equal(oracle.minmax(data, raw=True), raw, equal_nan=True)
+    got = oracle.minmax(data)
+    assert got.dtype == result.dtype and np.array_equal(got, result, equal_nan=True)
+
+
+def test_minmax_float_cast_quirk_is_in_the_golden_vectors():
+    # int32 max - 1 = 2147483646 is not a float32: the reference reports 2147483648.0 in its grid (vaex/cpu.py:519-531)
+    _, raw, _ = MINMAX["int32"]
+    assert raw[1] == 2147483648.0
+    _, raw, _ = MINMAX["int64"]
+    assert raw[1] == 9223372036854775808.0  # int64 goes through float64
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_minmax_matches_compiled_reference_random(seed, oracle, ref):
+    rng = np.random.default_rng(4000 + seed)
+    n = int(rng.integers(1, 20000))
+    for dt in ("f8", "f4", "i8", "i4", "i2", "i1", "u8", "u4", "u2", "u1", "?", ">f8", ">i4", ">u2"):
+        d = np.dtype(dt)
+        if d.kind == "f":
+            v = (rng.standard_normal(n) * 10.0 ** int(rng.integers(-3, 6))).astype(d)
+            v[rng.random(n) < 0.2] = np.nan
+        elif d.kind == "b":
+            v = rng.integers(0, 2, n).astype(d)
+        else:
+            info = np.iinfo(d)
+            v = rng.integers(info.min, info.max, n, dtype=np.int64 if d.kind == "i" else np.uint64, endpoint=True).astype(d)
+        for col in (v, np.ma.array(v, mask=rng.random(n) < 0.5)):
+            assert np.array_equal(oracle.minmax(col, raw=True), ref.minmax(col, raw=True), equal_nan=True), dt

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # VAEX_B200_LIB: load this build of the library instead of the in-tree one (A/B timing of kernel variants on one box)
 LIB_PATH = os.environ.get("VAEX_B200_LIB") or os.path.join(_HERE, "libb200agg.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "binby.cu", "fast.cu", "first.cu", "hashset.cu", "nunique.cu", "ringcount.cu", "tilecount.cu", "tilesort.cu"]
+SOURCES = ["api.cu", "binby.cu", "expr.cu", "fast.cu", "first.cu", "hashset.cu", "minmax.cu", "nunique.cu", "ringcount.cu", "tilecount.cu", "tilesort.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
@@ -34,6 +34,14 @@ class Binner(C.Structure):
     _fields_ = [("kind", C.c_int32), ("dtype", C.c_int32), ("byteswap", C.c_int32), ("allow_other", C.c_int32), ("invert", C.c_int32),
                 ("reserved", C.c_int32), ("vmin", C.c_double), ("vmax", C.c_double), ("bins", C.c_uint64), ("ordinal_count", C.c_int64),
                 ("min_value", C.c_int64), ("set", C.c_void_p), ("data", C.c_void_p), ("mask", C.c_void_p)]
+
+
+class ExprOp(C.Structure):
+    _fields_ = [("op", C.c_int32), ("cls", C.c_int32), ("arg", C.c_int32), ("reserved", C.c_int32), ("f", C.c_double), ("i", C.c_int64)]
+
+
+class ExprInput(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("dtype", C.c_int32), ("reserved", C.c_int32)]
 
 
 class AggInput(C.Structure):
@@ -110,6 +118,9 @@ def lib():
             "b200_agg_merge": (i32, [vp, P(vp), i32]),
             "b200_agg_write": (i32, [vp, vp]),
             "b200_bin": (i32, [vp, i32, P(Binner), i32, P(AggInput), i32, i64, i64, i32, u32]),
+            "b200_eval": (i32, [vp, i32, P(ExprOp), i32, P(ExprInput), i32, P(vp), i32, i64, i32, i32, vp]),
+            "b200_compact": (i32, [vp, i32, vp, i32, P(vp), P(i32), i64, i32, P(vp), P(i64)]),
+            "b200_set_dtype": (i32, [vp]),
             "b200_set_create": (i32, [vp, i32, i32, i64, P(vp)]),
             "b200_set_from_keys": (i32, [vp, i32, vp, i64, i64, i64, i64, P(vp)]),
             "b200_set_destroy": (i32, [vp]),

@@ -926,78 +926,5 @@ int b200_bin(b200_ctx *ctx, int slot, const b200_binner *binners, int nbinners, 
     return B200_OK;
 }
 
-// ---- limits pre-pass -------------------------------------------------------------------------------
 } // extern "C"
 
-namespace b200 {
-namespace {
-__global__ void __launch_bounds__(256) k_minmax(int dtype, int isz, int byteswap, const void *data, const uint8_t *mask, long long nrows, double *out) {
-    double lo = INFINITY, hi = -INFINITY;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += (long long)gridDim.x * blockDim.x) {
-        uint64_t raw;
-        switch (isz) {
-        case 8: raw = __ldcs(static_cast<const unsigned long long *>(data) + i); break;
-        case 4: raw = __ldcs(static_cast<const unsigned *>(data) + i); break;
-        case 2: raw = __ldcs(static_cast<const unsigned short *>(data) + i); break;
-        default: raw = __ldcs(static_cast<const unsigned char *>(data) + i); break;
-        }
-        if (byteswap)
-            raw = bswap(raw, isz);
-        if (mask && mask[i] == 1)
-            continue;
-        double v = raw_to_double(dtype, raw);
-        if (v != v)
-            continue;
-        lo = fmin(lo, v);
-        hi = fmax(hi, v);
-    }
-    for (int o = 16; o; o >>= 1) {
-        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    }
-    __shared__ double slo[8], shi[8];
-    if ((threadIdx.x & 31) == 0) {
-        slo[threadIdx.x >> 5] = lo;
-        shi[threadIdx.x >> 5] = hi;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; w++) {
-            lo = fmin(lo, slo[w]);
-            hi = fmax(hi, shi[w]);
-        }
-        atomic_min_f64(out, lo);
-        atomic_max_f64(out + 1, hi);
-    }
-}
-} // namespace
-} // namespace b200
-
-extern "C" int b200_minmax(b200_ctx *ctx, int slot, int dtype, int byteswap, const void *data, const uint8_t *mask, int64_t nrows, int memspace,
-                           double *out) {
-    if (!ctx || slot < 0 || slot >= ctx->nslots || dtype < 0 || dtype >= B200_NDTYPE || !out || (nrows && !data)) {
-        set_error("b200_minmax: invalid argument");
-        return B200_ERR_INVALID;
-    }
-    B200_CUDA(cudaSetDevice(ctx->device));
-    Slot *sl = ctx->slots[slot];
-    std::lock_guard<std::mutex> guard(sl->mu);
-    Stager stg{ctx, sl, memspace};
-    const int isz = dtype_size(dtype);
-    stg.plan(data, (size_t)nrows * isz);
-    if (mask)
-        stg.plan(mask, (size_t)nrows);
-    B200_CHECK(stg.commit());
-    double init[2] = {INFINITY, -INFINITY};
-    double *d = static_cast<double *>(sl->dscratch);
-    B200_CUDA(cudaMemcpyAsync(d, init, sizeof init, cudaMemcpyHostToDevice, sl->stream));
-    if (nrows) {
-        long long want = (nrows + 255) / 256;
-        int blocks = (int)std::min<long long>(want, (long long)ctx->sm_count * 8);
-        k_minmax<<<blocks, 256, 0, sl->stream>>>(dtype, isz, byteswap && isz > 1, stg.dev(data), static_cast<const uint8_t *>(stg.dev(mask)), nrows, d);
-        B200_CUDA(cudaGetLastError());
-    }
-    B200_CUDA(cudaMemcpyAsync(out, d, sizeof init, cudaMemcpyDeviceToHost, sl->stream));
-    B200_CUDA(cudaStreamSynchronize(sl->stream));
-    return B200_OK;
-}

@@ -16,6 +16,7 @@
 
 #include "binby.cuh"
 #include "device_utils.cuh"
+#include "scan.cuh"
 
 struct b200_set {
     b200_ctx *ctx = nullptr;
@@ -261,48 +262,6 @@ __global__ void __launch_bounds__(kRadixThreads) k_radix_hist(const unsigned lon
     }
     __syncthreads();
     hist[(unsigned long long)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
-}
-
-// exclusive scan of `n` counters in place (single CTA of 1024 threads: n is 256 x nblocks <= a few million)
-__global__ void __launch_bounds__(1024) k_scan_u32(unsigned *a, unsigned long long n) {
-    __shared__ unsigned warp_sums[32];
-    __shared__ unsigned carry;
-    if (threadIdx.x == 0)
-        carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned long long base = 0; base < n; base += 1024) {
-        const unsigned long long i = base + threadIdx.x;
-        const unsigned v = i < n ? a[i] : 0u;
-        unsigned x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o)
-                x += y;
-        }
-        if (lane == 31)
-            warp_sums[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned w = warp_sums[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o)
-                    w += y;
-            }
-            warp_sums[lane] = w;
-        }
-        __syncthreads();
-        const unsigned before = carry + (warp ? warp_sums[warp - 1] : 0u) + x - v;
-        if (i < n)
-            a[i] = before;
-        __syncthreads();
-        if (threadIdx.x == 1023)
-            carry = before + v;
-        __syncthreads();
-    }
 }
 
 __global__ void __launch_bounds__(kRadixThreads) k_radix_scatter(const unsigned long long *key, const unsigned long long *val, unsigned long long *key_out,
@@ -1008,6 +967,7 @@ SET_GETTER(nan_index, s->nan_value)
 SET_GETTER(null_index, s->null_value)
 
 int b200_set_nmaps(const b200_set *s) { return s ? s->nmaps : -1; }
+int b200_set_dtype(const b200_set *s) { return s ? s->dtype : -1; }
 
 int b200_set_offsets(b200_set *s, int64_t *out) {
     std::lock_guard<std::mutex> g(s->mu);

@@ -54,8 +54,11 @@ class Frame:
         self.categories[name] = (int(min_value), int(count))
 
     # ---- limits pre-pass ---------------------------------------------------------------------------------------------
-    def minmax(self, expression):
-        """df.minmax: NaN / masked values ignored (vaexfast OP_MIN_MAX, src/vaexfast.cpp:1089-1101) — on the device."""
+    def minmax(self, expression, raw=False):
+        """df.minmax(expression): the limits pre-pass, on the device (csrc/minmax.cu).  Masked rows and NaN are ignored; like the
+        reference (TaskStatistic(OP_MIN_MAX) over vaexfast.statisticNd, vaex/cpu.py:513-606) the reduction runs on the column cast
+        to float64 (float64 / int64 columns) or float32 (everything else) and the (min, max) pair is cast back to the column dtype
+        (vaex/dataframe.py:1524-1528).  raw=True returns the two doubles of the statistic grid."""
         import ctypes as C
         col = self.columns[expression]
         mask = None
@@ -66,7 +69,14 @@ class Frame:
         out = (C.c_double * 2)()
         ctx = _lib.context()
         _lib.check(_lib.lib().b200_minmax(ctx._h, 0, c.code, c.byteswap, c.ptr, None if mask is None else mask.ptr, c.length, c.memspace, out))
-        return np.array([out[0], out[1]])
+        res = np.array([out[0], out[1]])
+        if raw:
+            return res
+        dt = np.dtype(c.dtype).newbyteorder("=")
+        if dt.kind in "mM":
+            return res
+        with np.errstate(invalid="ignore"):
+            return res.astype(dt)
 
     def limits(self, expressions, value="minmax"):
         if isinstance(expressions, str):
@@ -98,7 +108,7 @@ class Frame:
                 continue
             lim = limits[i]
             if lim is None:
-                lim = self.minmax(b)  # the extra pass the reference runs for limits=None (dataframe.py:5618)
+                lim = self.minmax(b).astype("float64")  # the extra pass the reference runs for limits=None (dataframe.py:5618)
             specs.append({"binner-type": "scalar", "expression": b, "dtype": dtype.str, "count": int(shapes[i]), "minimum": float(lim[0]),
                           "maximum": float(lim[1])})
         return specs
