@@ -111,3 +111,52 @@ def test_device_virtual_columns_are_evaluated_per_chunk_on_the_workers_slot():
     Executor(nthreads=1, chunk_size=16).execute({"v": v}, [Task(part)], 40)
     assert [(a, b) for _, a, b in v.seen] == [(0, 16), (16, 32), (32, 40)]
     assert [c[6] for c in part.calls] == [float(np.arange(a, b).sum()) for _, a, b in v.seen]
+
+
+def test_progress_returning_false_cancels_the_pass():
+    """vaex/multithreading.py:111-118 + vaex/execution.py:478-482: a progress callback that returns exactly False stops the feed;
+    the tasks are marked cancelled and UserAbort is raised.  None / True keep going."""
+    from vaex_b200.execution import Executor, Task, UserAbort
+    n = 1000
+    cols = {"x": np.arange(n, dtype="f8"), "y": np.ones(n, dtype="i4")}
+    part = RecordingPart(["x", "y"])
+    task = Task(part, selections=[None, None])
+    seen = []
+
+    def progress(f):
+        seen.append(f)
+        return False if f >= 0.3 else None
+    with pytest.raises(UserAbort):
+        Executor(nthreads=1, chunk_size=100).execute(cols, [task], n, progress=progress)
+    assert task.cancelled and not part.reduced
+    assert len(part.calls) == 3 and seen[-1] == pytest.approx(0.3)
+    part2 = RecordingPart(["x", "y"])
+    Executor(nthreads=1, chunk_size=100).execute(cols, [Task(part2, selections=[None, None])], n, progress=lambda f: True)
+    assert part2.reduced and len(part2.calls) == 10
+
+
+def test_memory_declaration_is_cross_checked():
+    """vaex/execution.py:413-414: what a task part declares must be what it reports"""
+    from vaex_b200.execution import Executor, Task
+    part = RecordingPart(["x"])
+    part.predicted_memory_usage = 100
+    part.memory_usage = lambda: 96
+    with pytest.raises(RuntimeError, match="Reported memory usage"):
+        Executor(nthreads=1).execute({"x": np.zeros(10)}, [Task(part)], 10)
+
+
+def test_expression_compiler_follows_numpy_result_types():
+    """vaex_b200/expression.py decides every node's dtype by asking numpy (NEP 50 weak scalars included); unsupported syntax raises
+    at compile time instead of falling back to a host evaluation"""
+    from vaex_b200.expression import Program
+    dt = {"x": np.dtype("f4"), "y": np.dtype("f8"), "i": np.dtype("i4"), "j": np.dtype("i8"), "u": np.dtype("u1"), "h": np.dtype("i2")}
+    ns = {k: np.zeros(0, v) for k, v in dt.items()}
+    ns.update(abs=np.abs, sqrt=np.sqrt)
+    for e in ["x + y", "x * 2.5", "i + 1", "i * 2.5", "i / j", "x / 3", "(x - 1) * (y + 2) > 0.5", "(i > 3) & (x < 0.5)", "~(x > 0)", "-x", "abs(i)", "sqrt(i)",
+              "sqrt(x)", "h + h", "u * u", "x.astype('float64') + 1", "i + j", "u + i", "h * 100", "(x > 0) | (y != y)"]:
+        assert Program(e, dt).dtype == eval(e, dict(ns)).dtype, e
+    for bad in ["x ** 2", "x // 2", "log(x)", "x if y else 0", "x[0]", "x and y", "'a'"]:
+        with pytest.raises((NotImplementedError, SyntaxError)):
+            Program(bad, dt)
+    with pytest.raises(KeyError):
+        Program("nope + 1", dt)

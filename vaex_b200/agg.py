@@ -113,7 +113,16 @@ class AggregatorDescriptorBasic(AggregatorDescriptor):
         if ncells >= 1e6:
             grids = _min(8, nthreads)
         grids = _max(grids, 1)
-        return agg_op_type(grid, grids, nthreads, *self.agg_args)
+        # memory pre-declaration (vaex/agg.py:309-318): bytes_per_cell * cells * grids is declared before the aggregator exists and
+        # must equal what the object then reports
+        import sys
+        self.predicted_memory_usage = self.dtype_out.itemsize * ncells * grids
+        agg_op = agg_op_type(grid, grids, nthreads, *self.agg_args)
+        used_memory = agg_op.__sizeof__()
+        if used_memory != self.predicted_memory_usage:
+            raise RuntimeError(f"Wrong prediction for {agg_op_type}, expected to take {self.predicted_memory_usage} bytes but actually used {used_memory}")
+        self.predicted_memory_usage = sys.getsizeof(agg_op)  # what TaskPartAggregation.memory_usage() sums (vaex/cpu.py:649)
+        return agg_op
 
     def get_result(self, agg_operation):
         # vaex/agg.py:323-335: drop the edge cells unless edges=True (scalar [2:-1], ordinal [0:-2])

@@ -5,7 +5,10 @@
 // Shared-memory atomics retire ~6 lanes/clk/SM, 9x more, but a 1027^2 grid is 4 MB even with 32-bit counters.  So the grid is
 // cut into <= 32 (else 64) GRID TILES ("parts") of <= 49152 consecutive cells and the rows are partitioned by part first:
 //
-//   K1 k_ring_partition  every WARP is autonomous.  Columns are staged by TMA (cp.async.bulk + mbarrier, double buffered).
+//   K1 k_ring_partition  every WARP is autonomous.  The keys of the NEXT 256-row group are loaded into registers (128-bit,
+//                        evict-first loads) while the current group is placed; a TMA-staged variant (cp.async.bulk + mbarrier,
+//                        double buffered, as in round 1) was 8 % slower: 8.5 warp instructions per 32 rows went into issuing
+//                        the bulk copies and 4 KB of shared memory per warp into the buffers (profiles/r02_ncu_ring_v4.txt).
 //                        Per row: the bit-exact fp64 bin index, part = idx / tile_cells (one IMAD.HI), ONE shared-memory atomic
 //                        on the (warp, part) counter whose return value is the row's slot in that part's RING (96 entries), and
 //                        one 16-bit store of the local cell index into the ring.  Every 256 rows the rings that hold a full
@@ -78,46 +81,6 @@ constexpr int kMaxParts = 64;
 constexpr unsigned kNone = 0xFFFFFFFFu;
 constexpr int kCountThreads = 1024;
 
-// ---- TMA staging (cp.async.bulk global -> shared, completion on an mbarrier): each warp keeps the NEXT tile's columns in
-// flight while it works on the current one.  No registers, no LSU issue slots, and the copy engine sees >= 1 KB requests.
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
-                 "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    asm volatile("{\n\t"
-                 ".reg .pred P1;\n\t"
-                 "RING_WAIT_LOOP:\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-                 "@P1 bra RING_WAIT_DONE;\n\t"
-                 "bra RING_WAIT_LOOP;\n\t"
-                 "RING_WAIT_DONE:\n\t"
-                 "}" ::"r"(smem_u32(bar)),
-                 "r"(parity)
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-template <typename T>
-__device__ __forceinline__ void lds4(const T *buf, int i, T out[4]);
-template <>
-__device__ __forceinline__ void lds4<float>(const float *buf, int i, float out[4]) {
-    const float4 a = *reinterpret_cast<const float4 *>(buf + i);
-    out[0] = a.x, out[1] = a.y, out[2] = a.z, out[3] = a.w;
-}
-template <>
-__device__ __forceinline__ void lds4<double>(const double *buf, int i, double out[4]) {
-    const double2 a = *reinterpret_cast<const double2 *>(buf + i), b = *reinterpret_cast<const double2 *>(buf + i + 2);
-    out[0] = a.x, out[1] = a.y, out[2] = b.x, out[3] = b.y;
-}
 template <typename T>
 __device__ __forceinline__ void ldg4(const void *p, long long i, T out[4]);
 template <>
@@ -215,13 +178,12 @@ __device__ __forceinline__ unsigned group_rows_tail(const RingParams &p, long lo
     return worst;
 }
 
-// shared memory of one warp: [2 stages x ND columns x TILE rows of T] [rings: 32*PPL parts x (RING + 8) u16] [counters: 32*PPL u32]
+// shared memory of one warp: [rings: 32*PPL parts x (RING + 8) u16] [counters: 32*PPL u32] [flush map: 32 x {position, owner}]
 // A ring holds < 64 entries left over from the last flush + the new ones of one group; a flush moves whole LINES of 64 entries
 // (128 bytes).  With <= 32 new entries per part and group the ring never fills (the busiest part of the headline workload takes
 // 19 +- 4 of a group's 256 rows); rows that find it full go to direct REDs.
 template <typename T, int ND, int PPL, int FG>
 struct RingLayout {
-    static constexpr int kTileRows = kGroupRows * FG;
     static constexpr int kRing = kLine == 64 ? 96 : 64;
     static constexpr int kRingStride = kRing + 8; // 208 bytes: 16-byte aligned rows that rotate over the banks
     static constexpr size_t kColBytes = 0; // the keys travel through registers

@@ -34,6 +34,7 @@ class Task:
         self.selections = list(selections)
         self.result = None
         self.stopped = False
+        self.cancelled = False
 
 
 class Executor:
@@ -53,8 +54,15 @@ class Executor:
         one_pass = math.ceil(row_count / self.nthreads) if row_count else 1
         return min(self.chunk_size_max, max(self.chunk_size_min, one_pass))
 
-    def execute(self, columns, tasks, row_count=None, i0=0, progress=None):
-        """One pass over `columns` (dict name -> array) feeding every task part; returns [task.result...]."""
+    def execute(self, columns, tasks, row_count=None, i0=0, progress=None, filter=None):
+        """One pass over `columns` (dict name -> array) feeding every task part; returns [task.result...].
+
+        filter: a device-evaluated boolean expression (expression.DeviceExpression).  Per chunk the mask is computed on the
+                worker's slot and EVERY dependent column — and every selection mask — is compacted with it on the device before
+                the task parts see a row (vaex/execution.py:516-522); the parts get ``filter_mask`` and blocks of the kept length.
+        progress: called with the fraction done after every chunk; a return value of exactly ``False`` cancels the pass
+                (vaex/multithreading.py:111-118): no further chunk is fed, the tasks are marked cancelled and UserAbort is raised
+                (vaex/execution.py:478-482)."""
         if not tasks:
             return []
         needed = sorted({e for t in tasks for e in t.expressions})
@@ -64,24 +72,54 @@ class Executor:
         if row_count is None:
             row_count = len(columns[needed[0]]) if needed else 0
         self.passes += 1
-        device = needed and all(_is_device(columns[e]) or (getattr(columns[e], "device_virtual", False) and all(_is_device(c) for c in columns[e].columns)) for e in needed)
+        # memory pre-declaration cross-check (vaex/execution.py:413-414): what the parts report must be what their aggregators hold
+        for t in tasks:
+            declared = getattr(t.part, "predicted_memory_usage", None)
+            if declared is not None and declared != t.part.memory_usage():
+                raise RuntimeError(f"Reported memory usage by tasks was {t.part.memory_usage()}, while tracker listed {declared}")
+
+        def on_device(col):
+            if getattr(col, "device_virtual", False):
+                return all(_is_device(c) for c in col.columns)
+            return _is_device(col)
+        feed_cols = [columns[e] for e in needed] + ([filter] if filter is not None else []) + [s for t in tasks for s in t.selections if s is not None]
+        device = bool(feed_cols) and all(on_device(c) for c in feed_cols)
         errors = []
+        cancelled = threading.Event()
+
+        def block_of(col, thread_index, i1, i2):
+            # virtual columns evaluated on the device (hash.CombinedCodes, expression.DeviceExpression) are produced on this worker's slot
+            return col.chunk(thread_index, i1, i2) if getattr(col, "device_virtual", False) else col[i1:i2]
 
         def feed(thread_index, i1, i2):
+            if cancelled.is_set():
+                return 0
+            live = [t for t in tasks if not (t.stopped or t.part.stopped)]
             for t in tasks:
-                if t.stopped or t.part.stopped:
+                if t.part.stopped:
                     t.stopped = True
-                    continue
-                # virtual columns evaluated on the device (hash.CombinedCodes) are produced on this worker's slot
-                blocks = [columns[e].chunk(thread_index, i1, i2) if getattr(columns[e], "device_virtual", False) else columns[e][i1:i2] for e in t.expressions]
-                sel = [None if s is None else s[i1:i2] for s in t.selections]
+            raw = {e: block_of(columns[e], thread_index, i1, i2) for e in sorted({e for t in live for e in t.expressions})}
+            sels = {id(s): block_of(s, thread_index, i1, i2) for t in live for s in t.selections if s is not None}
+            filter_mask = None
+            if filter is not None and live:
+                from . import expression as _expr
+                filter_mask = filter.chunk(thread_index, i1, i2)
+                names, sel_ids = list(raw), list(sels)
+                kept, out = _expr.compact(thread_index, filter_mask, [raw[k] for k in names] + [_as_u8(sels[k]) for k in sel_ids])
+                raw = dict(zip(names, out[:len(names)]))
+                sels = dict(zip(sel_ids, out[len(names):]))
+                filter_mask.kept = kept  # count(*) has no block to take its length from
+            for t in live:
+                blocks = [raw[e] for e in t.expressions]
+                sel = [None if s is None else sels[id(s)] for s in t.selections]
                 try:
-                    t.part.process(thread_index, i0 + i1, i0 + i2, None, sel, blocks)
+                    if filter_mask is None or filter_mask.kept:
+                        t.part.process(thread_index, i0 + i1, i0 + i2, filter_mask, sel, blocks)
                 except Exception as e:  # stash and re-raise on the main thread (vaex/execution.py:567-571)
                     errors.append(e)
                     t.stopped = True
-            if progress is not None:
-                progress(i2 / max(row_count, 1))
+            if progress is not None and progress(i2 / max(row_count, 1)) is False:
+                cancelled.set()
             return i2 - i1
 
         if row_count:
@@ -109,10 +147,28 @@ class Executor:
                         list(pool.map(work, ranges))
         if errors:
             raise errors[0]
+        if cancelled.is_set():
+            for t in tasks:
+                t.cancelled = True
+            raise UserAbort("Task was cancelled")
         for t in tasks:
             t.part.reduce([])
             t.result = t.part.get_result()
         return [t.result for t in tasks]
+
+
+def _as_u8(mask):
+    """selection masks travel as one byte per row"""
+    if _is_device(mask):
+        return mask
+    m = np.asarray(mask)
+    if np.ma.isMaskedArray(mask):  # vaex.utils.unmask_selection_mask
+        m = mask.data & ~np.ma.getmaskarray(mask)
+    return np.ascontiguousarray(m).astype(np.bool_, copy=False).view(np.uint8)
+
+
+class UserAbort(Exception):
+    """vaex.execution.UserAbort: raised when a progress callback returned False"""
 
 
 def merge_aggregation_tasks(requests, dtypes, nthreads):

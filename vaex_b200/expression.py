@@ -360,6 +360,7 @@ class DeviceArray:
 
     def to_numpy(self):
         import torch
+        _lib.context().sync()  # the producing kernel runs on a slot's stream, torch copies on its own
         out = np.empty(self.length, self.dtype)
         if self.length:
             t = torch.as_tensor(self, device="cuda")

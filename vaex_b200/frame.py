@@ -27,18 +27,67 @@ def _dtype_of(ar):
 
 
 class Frame:
-    def __init__(self, columns, nthreads=None, executor=None, categories=None, pin=False):
-        """pin=True page-locks the host (numpy) columns once so that chunk uploads run at PCIe rate (b200_host_register)."""
+    def __init__(self, columns, nthreads=None, executor=None, categories=None, pin=False, filter=None, variables=None):
+        """pin=True page-locks the host (numpy) columns once so that chunk uploads run at PCIe rate (b200_host_register).
+        filter: boolean expression string — the frame then behaves like ``df[df.<expression>]`` (dataframe.py filtered frames):
+        every pass evaluates the filter on the device and compacts the dependent columns with it (vaex/execution.py:516-522)."""
         self.columns = dict(columns)
+        self.variables = dict(variables or {})  # names usable inside expressions (hash maps for _ordinal_values, ...)
+        self._filter_expression = filter
+        self._filter = None
         self._pinned = _lib.pinned(*[v for v in self.columns.values() if isinstance(v, np.ndarray) and not np.ma.isMaskedArray(v)]) if pin else None
         self.executor = executor or execution.Executor(nthreads)
         self.categories = dict(categories or {})  # name -> (min_value, count): ordinal-coded columns (df.categorize)
         n = {len(v) for v in self.columns.values()}
         assert len(n) <= 1, "all columns must have equal length"
         self.length = n.pop() if n else 0
+        if filter is not None:
+            self._filter = self.expression(filter)
+            if self._filter.dtype != np.bool_:
+                raise ValueError(f"filter {filter!r} is not a boolean expression (dtype {self._filter.dtype})")
 
     def __len__(self):
         return self.length
+
+    # ---- expressions: virtual columns, filters, selections — evaluated on the device (csrc/expr.cu) ----------------------------
+    def expression(self, text):
+        """compile `text` over this frame's columns into a device-evaluated column (expression.DeviceExpression)"""
+        from . import expression as _expr
+        real = {k: v for k, v in self.columns.items() if not isinstance(v, _expr.DeviceExpression)}
+        # virtual columns are substituted textually, like vaex expands them before evaluation
+        text = self._expand(str(text))
+        return _expr.DeviceExpression(text, real, self.variables)
+
+    def _expand(self, text):
+        import ast
+        from . import expression as _expr
+        virtual = {k: v.expression for k, v in self.columns.items() if isinstance(v, _expr.DeviceExpression)}
+        if not virtual:
+            return text
+
+        class Sub(ast.NodeTransformer):
+            def visit_Name(self, node):
+                if node.id in virtual:
+                    return ast.parse("(" + virtual[node.id] + ")", mode="eval").body
+                return node
+        return ast.unparse(Sub().visit(ast.parse(text, mode="eval")))
+
+    def add_virtual_column(self, name, expression):
+        """df.add_virtual_column / df['name'] = expression (dataframe.py:3476-3530): evaluated on the device, never materialised"""
+        self.columns[name] = self.expression(expression)
+
+    def filter(self, expression):
+        """df[df.<expression>]: a filtered view over the same columns (filters combine with &, dataframe.py:5535-5560)"""
+        combined = expression if self._filter_expression is None else f"({self._filter_expression}) & ({expression})"
+        f = Frame(self.columns, executor=self.executor, categories=self.categories, filter=combined, variables=self.variables)
+        return f
+
+    def evaluate(self, expression):
+        """host copy of an expression's values over the whole frame (unfiltered), chunked like every other pass"""
+        e = self.columns[expression] if expression in self.columns and getattr(self.columns[expression], "device_virtual", False) else self.expression(expression)
+        chunk = max(self.executor.chunk_size_for(self.length), 1)
+        parts = [e.chunk(0, i, min(i + chunk, self.length)).to_numpy() for i in range(0, self.length, chunk)]
+        return np.concatenate(parts) if parts else np.zeros(0, e.dtype)
 
     def __getitem__(self, name):
         return self.columns[name]
@@ -61,13 +110,37 @@ class Frame:
         (vaex/dataframe.py:1524-1528).  raw=True returns the two doubles of the statistic grid."""
         import ctypes as C
         col = self.columns[expression]
+        ctx = _lib.context()
+        out = (C.c_double * 2)()
+        if getattr(col, "device_virtual", False) or self._filter is not None:
+            # virtual columns and filtered frames: evaluate / compact chunk by chunk on the device, reduce every chunk
+            from . import expression as _expr
+            lo, hi, dt = np.inf, -np.inf, None
+            chunk = max(self.executor.chunk_size_for(self.length), 1) if not all(_is_device(c) for c in getattr(col, "columns", [col])) else max(self.length, 1)
+            for i1 in range(0, self.length, chunk):
+                i2 = min(i1 + chunk, self.length)
+                block = col.chunk(0, i1, i2) if getattr(col, "device_virtual", False) else col[i1:i2]
+                if self._filter is not None:
+                    if not _is_device(block) and np.ma.isMaskedArray(block):
+                        raise NotImplementedError("minmax of a masked column on a filtered frame")
+                    kept, (block,) = _expr.compact(0, self._filter.chunk(0, i1, i2), [block], ctx)
+                    if not kept:
+                        continue
+                c = _lib.column(block)
+                dt = c.dtype
+                _lib.check(_lib.lib().b200_minmax(ctx._h, 0, c.code, c.byteswap, c.ptr, None, c.length, c.memspace, out))
+                lo, hi = min(lo, out[0]), max(hi, out[1])
+            res = np.array([lo, hi])
+            if raw:
+                return res
+            dt = np.dtype(dt if dt is not None else _dtype_of(col)).newbyteorder("=")
+            with np.errstate(invalid="ignore"):
+                return res if dt.kind in "mM" else res.astype(dt)
         mask = None
         if not _is_device(col) and np.ma.isMaskedArray(col):
             mask = _lib.mask_column(np.ma.getmaskarray(col))
             col = np.ascontiguousarray(col.data)
         c = _lib.column(col)
-        out = (C.c_double * 2)()
-        ctx = _lib.context()
         _lib.check(_lib.lib().b200_minmax(ctx._h, 0, c.code, c.byteswap, c.ptr, None if mask is None else mask.ptr, c.length, c.memspace, out))
         res = np.array([out[0], out[1]])
         if raw:
@@ -113,12 +186,16 @@ class Frame:
                           "maximum": float(lim[1])})
         return specs
 
-    def _agg(self, aggregators, binby=None, limits=None, shape=128, selection=None, edges=False):
+    def _agg(self, aggregators, binby=None, limits=None, shape=128, selection=None, edges=False, progress=None):
         """Run several aggregators in as few passes as possible (equal binners -> one fused pass); returns their results."""
         single = not isinstance(aggregators, (list, tuple))
         aggregators = [aggregators] if single else list(aggregators)
         specs = self._binner_specs(binby, limits, shape)
         dtypes = self.dtypes()
+        if isinstance(selection, str):  # a selection expression: a boolean mask evaluated on the device per chunk
+            selection = self.expression(selection)
+            if selection.dtype != np.bool_:
+                raise ValueError("a selection must be a boolean expression")
         requests = []
         for a in aggregators:
             for prim in a.primitives():
@@ -126,7 +203,7 @@ class Frame:
                 prim.selection = None if selection is None else "selection"
                 requests.append((specs, prim, selection))
         tasks, pos = execution.merge_aggregation_tasks(requests, dtypes, self.executor.nthreads)
-        self.executor.execute(self.columns, tasks, self.length)
+        self.executor.execute(self.columns, tasks, self.length, filter=self._filter, progress=progress)
         results = []
         for a in aggregators:
             grids = []
@@ -136,8 +213,8 @@ class Frame:
             results.append(a.combine(*grids) if isinstance(a, _agg.AggregatorDescriptorMulti) else grids[0])
         return results[0] if single else results
 
-    def count(self, expression=None, binby=None, limits=None, shape=128, selection=None, edges=False):
-        return self._agg(_agg.count(expression or "*"), binby, limits, shape, selection, edges)
+    def count(self, expression=None, binby=None, limits=None, shape=128, selection=None, edges=False, progress=None):
+        return self._agg(_agg.count(expression or "*"), binby, limits, shape, selection, edges, progress=progress)
 
     def sum(self, expression, binby=None, limits=None, shape=128, selection=None, edges=False):
         return self._agg(_agg.sum(expression), binby, limits, shape, selection, edges)
@@ -243,7 +320,7 @@ class GroupBy:
             # nthreads=1 -> 7 shards, chunks fed in row order: the ordinals of the sequential reference run
             task = execution.Task(part)
             ex = execution.Executor(1, chunk_size_max=df.executor.chunk_size_max)
-            ex.execute(df.columns, [task], df.length)
+            ex.execute(df.columns, [task], df.length, filter=df._filter)
             hm = task.result
             if sort:
                 hm = hm.sorted()
@@ -272,7 +349,7 @@ class GroupBy:
         part = taskpart.TaskPartHashmapUniqueCreate(None, self._COMBINED, np.dtype("int64"), nthreads=1)
         task = execution.Task(part)
         ex = execution.Executor(1, chunk_size_max=df.executor.chunk_size_max)
-        ex.execute({self._COMBINED: codes}, [task], df.length)
+        ex.execute({self._COMBINED: codes}, [task], df.length, filter=df._filter)
         hm = task.result
         if self.sort:
             hm = hm.sorted()  # parents are sorted, so code order == lexicographic key order
@@ -303,7 +380,7 @@ class GroupBy:
         if self.combined is not None:
             codes, chm = self.combined
             columns[self._COMBINED] = codes
-            frame = Frame(columns, executor=df.executor)
+            frame = Frame(columns, executor=df.executor, categories=df.categories, filter=df._filter_expression, variables=df.variables)
             spec = {"binner-type": "hash", "expression": self._COMBINED, "dtype": "<i8", "hash_map_unique": chm}
             grids = frame._agg(descs, binby=[spec], edges=True)
             counts = grids[-1][:-2]
@@ -326,7 +403,7 @@ class GroupBy:
                 columns[cname] = codes
                 cdt = _dtype_of(codes)
                 specs.append({"binner-type": "ordinal", "expression": cname, "dtype": cdt.str, "count": len(hm), "minimum": 0, "invert": False})
-        frame = Frame(columns, executor=df.executor)
+        frame = Frame(columns, executor=df.executor, categories=df.categories, filter=df._filter_expression, variables=df.variables)
         grids = frame._agg(descs, binby=specs, edges=True)
         # _extract_center (vaex/groupby.py:896-977): drop the null / nan edge cells, keep groups with count > 0
         center = tuple(slice(0, -2) for _ in self.by)

@@ -73,6 +73,9 @@ class TaskPartAggregation(TaskPart):
             self.expressions.extend(d.expressions)
         self.grid = superagg.Grid([binner.copy() for binner in binners])
         self.nbytes = 0
+        # vaex/agg.py:311-318 pre-declares bytes_per_cell * cells * grids per aggregator and cross-checks it against the object;
+        # the executor compares the sum with memory_usage() (vaex/execution.py:413-414)
+        self.predicted_memory_usage = 0
         self.aggregations = []
         for i, d in enumerate(self.aggregation_descriptions):
             selection = d.selection
@@ -82,6 +85,7 @@ class TaskPartAggregation(TaskPart):
             for j, _ in enumerate(selections):
                 op = d._create_operation(self.grid, self.nthreads)
                 self.nbytes += sys.getsizeof(op)
+                self.predicted_memory_usage += getattr(d, "predicted_memory_usage", sys.getsizeof(op))
                 if initial_values is not None:
                     op.load(initial_values[i][j])  # vaex/cpu.py:654-658
                 ops.append(op)
@@ -99,8 +103,9 @@ class TaskPartAggregation(TaskPart):
     def process(self, thread_index, i1, i2, filter_mask, selection_masks, blocks):
         # vaex/cpu.py:678-786
         N = i2 - i1
-        if filter_mask is not None:
-            N = len(blocks[0]) if blocks else int(np.asarray(filter_mask).sum())
+        if filter_mask is not None:  # the executor compacted the blocks with the filter (vaex/execution.py:516-522)
+            kept = getattr(filter_mask, "kept", None)
+            N = len(blocks[0]) if blocks else (int(kept) if kept is not None else int(np.asarray(filter_mask).sum()))
         for block in blocks:
             assert len(block) == N, f"Oops, got a block of length {len(block)} while it is expected to be of length {N} (at {i1}-{i2}, filter={filter_mask is not None})"
         block_map = {expr: block for expr, block in zip(self.expressions, blocks)}
