@@ -176,6 +176,21 @@ int64_t b200_set_nan_index(b200_set *set);
 int64_t b200_set_null_index(b200_set *set);
 int b200_set_nmaps(const b200_set *set);
 int b200_set_dtype(const b200_set *set);
+
+/* ---- string key sets: vaex.superutils.ordered_set_string (src/hash_string.hpp:56-180, bound at src/hash_string.cpp:86-99) ---------
+ * Strings arrive in the arrow large_string layout StringList64 uses: int64 offsets[nrows + 1] into `bytes`, plus an optional byte
+ * mask (1 = null; the reference reads the arrow validity bitmap).  shard = std::hash<string_view>(key) % nmaps (libstdc++ 64-bit
+ * Murmur-2), ordinal = insertion rank in the shard, nulls join shard 0 at the end of the call that first sees one.  The getters
+ * b200_set_count / null_count / null_index / offsets / nmaps / destroy apply.  A 64-bit hash collision between two different
+ * strings is detected and reported (B200_ERR_UNSUPPORTED), never merged silently. */
+int b200_strset_create(b200_ctx *ctx, int nmaps, int64_t limit /* must be -1 */, b200_set **out);
+int b200_strset_update(b200_set *set, int slot, const int64_t *offsets, const uint8_t *bytes, const uint8_t *masks, int64_t nrows, int return_values,
+                       int64_t *out_values /* local ordinals */, int16_t *out_map_index, int memspace);
+/* global ordinals (-1: not a member); out is host memory, or a device buffer when out_is_device (consume it on the same slot) */
+int b200_strset_map_ordinal(b200_set *set, int slot, const int64_t *offsets, const uint8_t *bytes, const uint8_t *masks, int64_t nrows, int64_t *out,
+                            int memspace, int out_is_device);
+int b200_strset_key_bytes(b200_set *set, int64_t *nbytes_out);
+int b200_strset_key_array(b200_set *set, int64_t *offsets_out /* count + 1 */, uint8_t *bytes_out /* key_bytes */);
 int b200_set_offsets(b200_set *set, int64_t *out /* nmaps */);
 int b200_set_key_array(b200_set *set, void *keys_out /* count * itemsize, host */);
 /* out dtype follows the reference: count < 2^7 -> I8, < 2^15 -> I16, < 2^31 -> I32, else I64 */

@@ -406,3 +406,93 @@ def minmax(data, raw=False):
         return out
     with np.errstate(invalid="ignore"):
         return out.astype(data.dtype.newbyteorder("="))
+
+
+# ------------------------------------------------------------------------------------------------
+# string key sets: ordered_set<> over StringList64, restated (small cases: pure Python)
+# ------------------------------------------------------------------------------------------------
+_MUL = ((0xc6a4a793 << 32) + 0x5bd1e995) & 0xFFFFFFFFFFFFFFFF
+_M64 = 0xFFFFFFFFFFFFFFFF
+
+
+def string_hash(data: bytes) -> int:
+    """std::hash<string_view> of the reference build (src/hash.hpp:59-86 -> string-view-lite -> libstdc++ _Hash_bytes: the 64-bit
+    Murmur-2 variant, seed 0xc70f6907); pinned against the compiled reference in tests/test_oracle_pinning.py"""
+    n = len(data)
+    h = (0xc70f6907 ^ (n * _MUL)) & _M64
+    body = n & ~7
+    for p in range(0, body, 8):
+        d = int.from_bytes(data[p:p + 8], "little")
+        d = (d * _MUL) & _M64
+        d ^= d >> 47
+        d = (d * _MUL) & _M64
+        h = ((h ^ d) * _MUL) & _M64
+    if n & 7:
+        h = ((h ^ int.from_bytes(data[body:], "little")) * _MUL) & _M64
+    h ^= h >> 47
+    h = (h * _MUL) & _M64
+    h ^= h >> 47
+    return h
+
+
+class StringOrderedSet:
+    """ordered_set<> for strings (src/hash_string.hpp:56-180 update, :437-560 ordered_set): shard = hash % nmaps, ordinal = insertion
+    rank within the shard; nulls go to shard 0 at the END of the update call that first sees one; global ordinal = local + offsets."""
+
+    def __init__(self, nmaps=1):
+        self.nmaps = nmaps
+        self.maps = [dict() for _ in range(nmaps)]  # str -> local ordinal (insertion ordered)
+        self.null_count = 0
+        self.null_value = 0x7fffffff
+
+    def update(self, strings, start_index=0, return_values=False):
+        n = len(strings)
+        values, map_index = np.zeros(n, np.int64), np.zeros(n, np.int16)
+        buckets = [[] for _ in range(self.nmaps)]
+        nulls = []
+        for i, s in enumerate(strings):
+            if s is None:
+                nulls.append(i)
+            else:
+                buckets[string_hash(s.encode("utf8")) % self.nmaps].append(i)
+        for m, rows in enumerate(buckets):
+            for i in rows:
+                mp = self.maps[m]
+                if strings[i] not in mp:
+                    mp[strings[i]] = len(mp)  # add_new: map.size(); the null of shard 0 is one of its entries
+                values[i], map_index[i] = mp[strings[i]], m
+        for i in nulls:
+            if self.null_count == 0:
+                self.null_value = len(self.maps[0])
+                self.maps[0][None] = self.null_value
+            self.null_count += 1
+            values[i], map_index[i] = self.null_value, 0
+        return (values, map_index) if return_values else None
+
+    def offsets(self):
+        out, acc = [], 0
+        for mp in self.maps:
+            out.append(acc)
+            acc += len(mp)
+        return out
+
+    def keys(self):
+        return [k for mp in self.maps for k in mp]
+
+    def __len__(self):
+        return sum(len(mp) for mp in self.maps)
+
+    @property
+    def null_index(self):
+        return self.null_value  # 0x7fffffff until a null was seen (src/hash_string.hpp ordered_set<>::null_index)
+
+    def map_ordinal(self, strings):
+        off = self.offsets()
+        out = np.empty(len(strings), np.int64)
+        for i, s in enumerate(strings):
+            if s is None:
+                out[i] = self.null_value if self.null_count else -1
+            else:
+                m = string_hash(s.encode("utf8")) % self.nmaps
+                out[i] = off[m] + self.maps[m][s] if s in self.maps[m] else -1
+        return out

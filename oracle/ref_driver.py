@@ -301,3 +301,55 @@ def minmax(data, raw=False, chunk=1024 * 1024):
         return grid
     with np.errstate(invalid="ignore"):
         return grid.astype(np.asarray(data).dtype.newbyteorder("="))
+
+
+# ---- string key sets: ordered_set<> over StringList64 (src/hash_string.hpp) through oracle/ref_strset_shim.cpp ----------------
+def pack_strings(strings):
+    """list of str / None -> (int64 offsets[n+1], uint8 bytes, uint8 null mask): the arrow large_string layout StringList64 uses"""
+    enc = [(s.encode("utf8") if s is not None else b"") for s in strings]
+    off = np.zeros(len(enc) + 1, np.int64)
+    if enc:
+        off[1:] = np.cumsum([len(e) for e in enc])
+    by = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if off[-1] else np.zeros(0, np.uint8)
+    return off, by, np.array([s is None for s in strings], np.uint8)
+
+
+def unpack_strings(offsets, data, nulls=None):
+    return [None if (nulls is not None and nulls[i]) else bytes(data[offsets[i]:offsets[i + 1]]).decode("utf8") for i in range(len(offsets) - 1)]
+
+
+def strset_module():
+    import glob
+    if not glob.glob(os.path.join(_REF, "strset_shim*.so")):
+        raise RuntimeError("compiled string-set shim missing: run `make -C oracle ref` where /root/reference exists")
+    sys.path.insert(0, _REF)
+    try:
+        return importlib.import_module("strset_shim")
+    finally:
+        sys.path.remove(_REF)
+
+
+class RefStringSet:
+    """vaex.superutils.ordered_set_string(nmaps) of the compiled reference, fed with Python string lists"""
+
+    def __init__(self, nmaps=1, limit=-1):
+        self._s = strset_module().ordered_set_string(nmaps, limit)
+
+    def update(self, strings, start_index=0, return_values=False):
+        return self._s.update(*pack_strings(strings), start_index, return_values)
+
+    def map_ordinal(self, strings):
+        return np.asarray(self._s.map_ordinal(*pack_strings(strings)))
+
+    def keys(self):
+        off, by, nulls = self._s.key_array()
+        return unpack_strings(np.asarray(off), np.asarray(by), np.asarray(nulls))
+
+    def offsets(self):
+        return list(self._s.offsets())
+
+    def __len__(self):
+        return len(self._s)
+
+    null_count = property(lambda self: self._s.null_count)
+    null_index = property(lambda self: self._s.null_index)

@@ -57,3 +57,20 @@ def load_minmax():
             data = np.ma.array(data, mask=z[name + "/mask"])
         out[name] = (data, z[name + "/raw"], z[name + "/result"])
     return out
+
+
+STRINGS_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "strings_golden.npz")
+
+
+def unpack_strings(offsets, data, nulls=None):
+    return [None if (nulls is not None and len(nulls) and nulls[i]) else bytes(data[offsets[i]:offsets[i + 1]]).decode("utf8") for i in range(len(offsets) - 1)]
+
+
+def load_strings():
+    """tests/golden/strings_golden.npz (tests/golden/make_golden_strings.py): name -> dict of arrays"""
+    z = np.load(STRINGS_PATH, allow_pickle=False)
+    cases = {}
+    for key in z.files:
+        name, field = key.split("/", 1)
+        cases.setdefault(name, {})[field] = z[key]
+    return cases

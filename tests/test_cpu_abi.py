@@ -57,12 +57,11 @@ def test_mirror_class_names_match_reference(ref):
     assert not [n for n in sets if not hasattr(myutils, n)]
 
 
-def test_out_of_scope_names_raise():
-    from vaex_b200 import superagg
+def test_string_names_resolve_and_object_names_raise():
+    from vaex_b200 import superagg, superutils
+    assert superagg.AggNUnique_string and superagg.AggCount_string and superutils.ordered_set_string  # round 2: string keys on the device
     with pytest.raises(AttributeError):
-        superagg.AggNUnique_string
-    with pytest.raises(AttributeError):
-        superagg.AggList_int32
+        superagg.AggCount_object
 
 
 def test_no_cpu_fallback():

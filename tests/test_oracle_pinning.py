@@ -126,3 +126,29 @@ def test_oracle_minmax_matches_compiled_reference_random(seed, oracle, ref):
             v = rng.integers(info.min, info.max, n, dtype=np.int64 if d.kind == "i" else np.uint64, endpoint=True).astype(d)
         for col in (v, np.ma.array(v, mask=rng.random(n) < 0.5)):
             assert np.array_equal(oracle.minmax(col, raw=True), ref.minmax(col, raw=True), equal_nan=True), dt
+
+
+# ---- string key sets ----------------------------------------------------------------------------------
+STRINGS = golden_util.load_strings()
+
+
+def test_string_hash_known_answers(oracle):
+    """std::hash<string_view> of the reference build = libstdc++'s 64-bit Murmur-2 (src/hash.hpp:59-86)"""
+    c = STRINGS["strhash"]
+    keys = [bytes(c["bytes"][c["offsets"][i]:c["offsets"][i + 1]]) for i in range(len(c["offsets"]) - 1)]
+    assert [oracle.string_hash(k) for k in keys] == [int(h) for h in c["hash"]]
+
+
+@pytest.mark.parametrize("name", sorted(k for k in STRINGS if k.startswith("strset_")))
+def test_oracle_string_set_matches_golden(name, oracle):
+    c = STRINGS[name]
+    s = oracle.StringOrderedSet(int(name.split("_")[1]))
+    for k in range(int(c["ncalls"])):
+        strs = golden_util.unpack_strings(c[f"c{k}_offsets"], c[f"c{k}_bytes"], c[f"c{k}_mask"])
+        vals, mi = s.update(strs, 0, True)
+        assert np.array_equal(vals, c[f"c{k}_values"]) and np.array_equal(mi, c[f"c{k}_map_index"])
+    assert s.keys() == golden_util.unpack_strings(c["key_offsets"], c["key_bytes"], c["key_nulls"])
+    assert s.offsets() == c["shard_offsets"].tolist()
+    probe = golden_util.unpack_strings(c["probe_offsets"], c["probe_bytes"], c["probe_mask"])
+    assert np.array_equal(s.map_ordinal(probe), c["probe_ordinals"])
+    assert [len(s), s.null_count, s.null_index] == c["info"].tolist()

@@ -121,6 +121,11 @@ def lib():
             "b200_eval": (i32, [vp, i32, P(ExprOp), i32, P(ExprInput), i32, P(vp), i32, i64, i32, i32, vp]),
             "b200_compact": (i32, [vp, i32, vp, i32, P(vp), P(i32), i64, i32, P(vp), P(i64)]),
             "b200_set_dtype": (i32, [vp]),
+            "b200_strset_create": (i32, [vp, i32, i64, P(vp)]),
+            "b200_strset_update": (i32, [vp, i32, vp, vp, vp, i64, i32, vp, vp, i32]),
+            "b200_strset_map_ordinal": (i32, [vp, i32, vp, vp, vp, i64, vp, i32, i32]),
+            "b200_strset_key_bytes": (i32, [vp, P(i64)]),
+            "b200_strset_key_array": (i32, [vp, vp, vp]),
             "b200_set_create": (i32, [vp, i32, i32, i64, P(vp)]),
             "b200_set_from_keys": (i32, [vp, i32, vp, i64, i64, i64, i64, P(vp)]),
             "b200_set_destroy": (i32, [vp]),

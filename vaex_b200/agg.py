@@ -31,6 +31,11 @@ def _upcast(dtype):
 def find_type_from_dtype(namespace, prefix, dtype, *others):
     """vaex.utils.find_type_from_dtype (vaex/utils.py:754-791): ``prefix + dtype [+ '_' + dtype2] [+ '_non_native']``."""
     dtype = np.dtype(dtype)
+    if dtype.kind in "OU":  # string columns: the reference's classes carry the suffix "string"
+        name = prefix + "string"
+        if not hasattr(namespace, name):
+            raise ValueError(f"Could not find a class ({name}), seems strings are not supported.")
+        return getattr(namespace, name)
     if dtype.kind in "mM":
         dtype = np.dtype("int64") if dtype.kind == "m" else np.dtype("uint64")
     name = prefix + dtype.newbyteorder("=").name

@@ -18,6 +18,13 @@
 #include "device_utils.cuh"
 #include "scan.cuh"
 
+namespace b200 {
+struct StrLog {
+    unsigned long long hash, off;
+    unsigned len, pad;
+};
+} // namespace b200
+
 struct b200_set {
     b200_ctx *ctx = nullptr;
     int dtype = 0, nmaps = 1;
@@ -39,6 +46,16 @@ struct b200_set {
     unsigned long long *d_keys_ord = nullptr; // n_entries canonical patterns in ordinal order (device)
     uint64_t n_entries = 0;                   // keys + NaN + null slots
     int64_t max_call_rows = 0;                // largest update so far: bounds the row part of every tag
+    // string keys (ordered_set_string): the table's key is the reference's 64-bit string hash; the bytes of every distinct key live
+    // in `pool`, described by `log` (one record per key, in claim order); slot_log[table slot] = index of the key's record
+    bool strings = false;
+    char *pool = nullptr;
+    uint64_t pool_cap = 0;
+    b200::StrLog *log = nullptr;
+    unsigned *slot_log = nullptr;            // parallel to `table`
+    unsigned long long *d_strctr = nullptr;  // [0] records in `log`, [1] bytes used in `pool`
+    unsigned long long *d_str_off = nullptr; // finalized: pool offset of the key with ordinal i
+    unsigned *d_str_len = nullptr;
     std::vector<int64_t> h_offsets;
     int64_t n_keys = 0, nan_count = 0, null_count = 0;
     int64_t nan_value = 0x7fffffff, null_value = 0x7fffffff; // src/hash_primitives.hpp:447
@@ -48,7 +65,7 @@ struct b200_set {
 
 namespace b200 {
 
-enum { CTR_COUNT = 0, CTR_OVERFLOW, CTR_NAN_COUNT, CTR_NULL_COUNT, CTR_NAN_TAG, CTR_NULL_TAG, CTR_SENTINEL_TAG, CTR_CURSOR, CTR_SENTINEL_COUNT, CTR_N };
+enum { CTR_COUNT = 0, CTR_OVERFLOW, CTR_NAN_COUNT, CTR_NULL_COUNT, CTR_NAN_TAG, CTR_NULL_TAG, CTR_SENTINEL_TAG, CTR_CURSOR, CTR_SENTINEL_COUNT, CTR_STR_ERROR /* 1: hash == empty pattern, 2: two strings share a 64-bit hash */, CTR_N };
 
 namespace {
 
@@ -206,7 +223,7 @@ __global__ void k_set_init(SetSlot *table, unsigned long long cap) {
 }
 
 __global__ void k_set_rehash(const SetSlot *old, unsigned long long old_cap, SetSlot *table, unsigned long long mask, const unsigned long long *old_counts,
-                             unsigned long long *counts) {
+                             unsigned long long *counts, const unsigned *old_aux = nullptr, unsigned *aux = nullptr) {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < old_cap; i += (unsigned long long)gridDim.x * blockDim.x) {
         unsigned long long k = old[i].key;
         if (k == SET_EMPTY)
@@ -217,6 +234,8 @@ __global__ void k_set_rehash(const SetSlot *old, unsigned long long old_cap, Set
         table[h].first = old[i].first;
         if (counts)
             counts[h] = old_counts[i];
+        if (aux)
+            aux[h] = old_aux[i];
     }
 }
 
@@ -432,6 +451,8 @@ int set_alloc_table(b200_set *s, uint64_t cap, cudaStream_t st) {
         B200_CUDA(cudaMalloc(&s->counts, cap * sizeof(unsigned long long)));
         B200_CUDA(cudaMemsetAsync(s->counts, 0, cap * sizeof(unsigned long long), st));
     }
+    if (s->strings)
+        B200_CUDA(cudaMalloc(&s->slot_log, cap * sizeof(unsigned)));
     k_set_init<<<nblocks(cap), 256, 0, st>>>(s->table, cap);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
@@ -440,14 +461,25 @@ int set_alloc_table(b200_set *s, uint64_t cap, cudaStream_t st) {
 int set_grow(b200_set *s, cudaStream_t st) {
     SetSlot *old = s->table;
     unsigned long long *old_counts = s->counts;
+    unsigned *old_slot_log = s->slot_log;
+    StrLog *old_log = s->log;
     uint64_t old_cap = s->cap;
     B200_CHECK(set_alloc_table(s, old_cap * 4, st));
-    k_set_rehash<<<nblocks(old_cap), 256, 0, st>>>(old, old_cap, s->table, s->cap - 1, old_counts, s->counts);
+    k_set_rehash<<<nblocks(old_cap), 256, 0, st>>>(old, old_cap, s->table, s->cap - 1, old_counts, s->counts, old_slot_log, s->slot_log);
     B200_CUDA(cudaGetLastError());
+    if (s->strings) { // one record per key at most: the log is as long as the table
+        B200_CUDA(cudaMalloc(&s->log, s->cap * sizeof(StrLog)));
+        if (old_log)
+            B200_CUDA(cudaMemcpyAsync(s->log, old_log, old_cap * sizeof(StrLog), cudaMemcpyDeviceToDevice, st));
+    }
     B200_CUDA(cudaStreamSynchronize(st));
     B200_CUDA(cudaFree(old));
     if (old_counts)
         B200_CUDA(cudaFree(old_counts));
+    if (old_slot_log)
+        B200_CUDA(cudaFree(old_slot_log));
+    if (old_log)
+        B200_CUDA(cudaFree(old_log));
     return B200_OK;
 }
 
@@ -456,6 +488,10 @@ int read_ctr(b200_set *s, cudaStream_t st, unsigned long long *h) {
     B200_CUDA(cudaStreamSynchronize(st));
     return B200_OK;
 }
+
+// the shard of a key is key_hash(dtype, key) % nmaps; a string set's table key already IS the reference's string hash, and the
+// 16-bit integer types use the identity there too (src/hash.hpp:50-152)
+static int shard_dtype(const b200_set *s) { return s->strings ? B200_U16 : s->dtype; }
 
 // lazily materialise ordinals; caller holds s->mu.  Everything stays on the device: compact -> radix sort by first-occurrence tag
 // (only the bytes that vary) -> stable radix pass(es) by shard -> position == global ordinal (src/hash.hpp:337-353) -> keys in
@@ -470,7 +506,7 @@ int set_finalize(b200_set *s) {
     unsigned long long zero = 0;
     // the insert kernel keeps no fill counter (see table_insert): count the occupied slots first, then compact them
     B200_CUDA(cudaMemcpyAsync(s->d_ctr + CTR_CURSOR, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
-    k_set_compact<<<nblocks(s->cap), 256, 0, st>>>(s->table, s->cap, s->d_ctr, nullptr, nullptr, nullptr, s->dtype, s->nmaps);
+    k_set_compact<<<nblocks(s->cap), 256, 0, st>>>(s->table, s->cap, s->d_ctr, nullptr, nullptr, nullptr, shard_dtype(s), s->nmaps);
     B200_CHECK(read_ctr(s, st, h));
     h[CTR_COUNT] = h[CTR_CURSOR];
     B200_CUDA(cudaMemcpyAsync(s->d_ctr + CTR_CURSOR, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
@@ -491,7 +527,7 @@ int set_finalize(b200_set *s) {
     unsigned *hist = reinterpret_cast<unsigned *>(work + off_hist);
     long long *d_first = reinterpret_cast<long long *>(work + off_first), *d_spec = reinterpret_cast<long long *>(work + off_spec);
     if (n_table)
-        k_set_compact<<<nblocks(s->cap), 256, 0, st>>>(s->table, s->cap, s->d_ctr, ckey, tagA, valA, s->dtype, s->nmaps);
+        k_set_compact<<<nblocks(s->cap), 256, 0, st>>>(s->table, s->cap, s->d_ctr, ckey, tagA, valA, shard_dtype(s), s->nmaps);
     // the special entries ride along behind the table's keys: [key == SET_EMPTY pattern] [NaN] [null]; NaN / null live in shard 0
     unsigned long long xk[3], xt[3], xv[3];
     int ne = 0, sent_idx = -1, nan_idx = -1, null_idx = -1;
@@ -505,7 +541,7 @@ int set_finalize(b200_set *s) {
     };
     if (has_sent) {
         sent_idx = ne;
-        xk[ne] = SET_EMPTY, xt[ne] = h[CTR_SENTINEL_TAG], xv[ne] = ((key_hash(s->dtype, SET_EMPTY) % (unsigned long long)s->nmaps) << 32) | (n_table + ne);
+        xk[ne] = SET_EMPTY, xt[ne] = h[CTR_SENTINEL_TAG], xv[ne] = ((key_hash(shard_dtype(s), SET_EMPTY) % (unsigned long long)s->nmaps) << 32) | (n_table + ne);
         ne++;
     }
     if (has_nan) {
@@ -707,7 +743,7 @@ int b200_set_create(b200_ctx *ctx, int dtype, int nmaps, int64_t limit, b200_set
         return rc;
     }
     B200_CUDA(cudaMalloc(&s->d_ctr, sizeof(unsigned long long) * CTR_N));
-    unsigned long long init[CTR_N] = {0, 0, 0, 0, ~0ull, ~0ull, ~0ull, 0, 0};
+    unsigned long long init[CTR_N] = {0, 0, 0, 0, ~0ull, ~0ull, ~0ull, 0, 0, 0};
     B200_CUDA(cudaMemcpyAsync(s->d_ctr, init, sizeof init, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaStreamSynchronize(st));
     *out = s;
@@ -765,6 +801,12 @@ int b200_set_destroy(b200_set *s) {
     cudaFree(s->counts);
     cudaFree(s->probe);
     cudaFree(s->d_keys_ord);
+    cudaFree(s->pool);
+    cudaFree(s->log);
+    cudaFree(s->slot_log);
+    cudaFree(s->d_strctr);
+    cudaFree(s->d_str_off);
+    cudaFree(s->d_str_len);
     cudaFree(s->d_ctr);
     cudaFree(s->d_offsets);
     delete s;
@@ -1130,5 +1172,473 @@ size_t b200_set_bytes(b200_set *s) {
 }
 
 uint64_t b200_hash64(uint64_t x) { return hash64(x); }
+
+} // extern "C"
+
+// =====================================================================================================================================
+// string keys: ordered_set_string (src/hash_string.hpp:56-180 update, ordered_set<> :437-560)
+// =====================================================================================================================================
+// Reference: shard = std::hash<string_view>(key) % nmaps (libstdc++'s 64-bit Murmur-2, seed 0xc70f6907), ordinal = insertion rank
+// in the shard, nulls join shard 0 at the end of the update call that first sees one, key_array() = the shards' strings back to
+// back.  Device design: the set's table is keyed by that 64-bit hash (so shards and ordinals come out of the SAME finalisation as
+// the numeric sets); the thread that claims a slot appends the key's bytes to a pool and logs {hash, offset, length}; a second
+// kernel re-probes every row and compares its bytes with the pooled key, so two strings that share a 64-bit hash are DETECTED
+// (error, never a silent merge).  Strings arrive in the arrow large_string layout (int64 offsets + bytes) plus a byte mask.
+namespace b200 {
+namespace {
+
+__device__ __forceinline__ unsigned long long murmur64(const unsigned char *p, unsigned long long len) {
+    const unsigned long long mul = (0xc6a4a793ull << 32) + 0x5bd1e995ull;
+    unsigned long long h = 0xc70f6907ull ^ (len * mul);
+    const unsigned long long body = len & ~7ull;
+    for (unsigned long long i = 0; i < body; i += 8) {
+        unsigned long long d = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) // unaligned little-endian load
+            d |= (unsigned long long)p[i + b] << (8 * b);
+        d *= mul;
+        d ^= d >> 47;
+        d *= mul;
+        h ^= d;
+        h *= mul;
+    }
+    if (len & 7) {
+        unsigned long long d = 0;
+        for (unsigned b = 0; b < (len & 7); b++)
+            d |= (unsigned long long)p[body + b] << (8 * b);
+        h ^= d;
+        h *= mul;
+    }
+    h ^= h >> 47;
+    h *= mul;
+    h ^= h >> 47;
+    return h;
+}
+
+__global__ void __launch_bounds__(256) k_str_insert(SetSlot *table, unsigned long long mask, unsigned long long *ctr, unsigned long long *strctr, StrLog *log,
+                                                    char *pool, unsigned *slot_log, const long long *offsets, const unsigned char *bytes, const uint8_t *masks,
+                                                    long long base, long long row0, long long nrows, unsigned long long tag_base, int skip,
+                                                    unsigned long long null_low) {
+    unsigned long long n_null = 0, t_null = ~0ull;
+    bool dead = false;
+    unsigned it = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += (long long)gridDim.x * blockDim.x) {
+        if (!dead && (it++ & 31) == 0 && *reinterpret_cast<volatile unsigned long long *>(ctr + CTR_OVERFLOW))
+            dead = true;
+        if (dead && (skip & 2))
+            return;
+        const long long row = row0 + i;
+        if (masks && masks[row]) {
+            if (!(skip & 2)) {
+                n_null++;
+                t_null = min(t_null, tag_base | null_low);
+            }
+            continue;
+        }
+        if (dead)
+            continue;
+        const long long b = offsets[row] - base, e = offsets[row + 1] - base;
+        const unsigned long long len = (unsigned long long)(e - b);
+        const unsigned long long h = murmur64(bytes + b, len);
+        if (h == SET_EMPTY) { // one pattern in 2^64 is the table's "empty" marker
+            ctr[CTR_STR_ERROR] = 1;
+            continue;
+        }
+        const unsigned long long tag = tag_base | (unsigned long long)row;
+        unsigned long long pos = hash64(h) & mask;
+        bool done = false;
+        for (int step = 0; step < kMaxProbe && !done; step++) {
+            const ulonglong2 slot = __ldcg(reinterpret_cast<const ulonglong2 *>(table + pos));
+            unsigned long long k = slot.x, first = slot.y;
+            if (k == SET_EMPTY) {
+                k = atomicCAS(&table[pos].key, SET_EMPTY, h);
+                if (k == SET_EMPTY) { // this thread owns the new key: pool its bytes, log it
+                    k = h;
+                    first = ~0ull;
+                    const unsigned long long li = atomicAdd(strctr + 0, 1ull), po = atomicAdd(strctr + 1, len);
+                    for (unsigned long long c = 0; c < len; c++)
+                        pool[po + c] = (char)bytes[b + c];
+                    log[li].hash = h, log[li].off = po, log[li].len = (unsigned)len;
+                    slot_log[pos] = (unsigned)li;
+                }
+            }
+            if (k == h) {
+                if (tag < first)
+                    atomicMin(&table[pos].first, tag);
+                done = true;
+            } else {
+                pos = (pos + 1) & mask;
+            }
+        }
+        if (!done) {
+            if (!*reinterpret_cast<volatile unsigned long long *>(ctr + CTR_OVERFLOW))
+                ctr[CTR_OVERFLOW] = 1ull;
+            dead = true;
+        }
+    }
+    if (n_null) {
+        atomicAdd(ctr + CTR_NULL_COUNT, n_null);
+        atomicMin(ctr + CTR_NULL_TAG, t_null);
+    }
+}
+
+__device__ __forceinline__ bool bytes_equal(const char *a, const unsigned char *b, unsigned long long len) {
+    for (unsigned long long c = 0; c < len; c++)
+        if ((unsigned char)a[c] != b[c])
+            return false;
+    return true;
+}
+
+// every row against the pooled bytes of the key its hash selected: a mismatch is a 64-bit hash collision
+__global__ void __launch_bounds__(256) k_str_verify(const SetSlot *table, unsigned long long mask, unsigned long long *ctr, const StrLog *log, const char *pool,
+                                                    const unsigned *slot_log, const long long *offsets, const unsigned char *bytes, const uint8_t *masks,
+                                                    long long base, long long nrows) {
+    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += (long long)gridDim.x * blockDim.x) {
+        if (masks && masks[row])
+            continue;
+        const long long b = offsets[row] - base;
+        const unsigned long long len = (unsigned long long)(offsets[row + 1] - offsets[row]);
+        const unsigned long long h = murmur64(bytes + b, len);
+        if (h == SET_EMPTY)
+            continue;
+        unsigned long long pos = hash64(h) & mask;
+        while (true) {
+            const unsigned long long k = table[pos].key;
+            if (k == h) {
+                const StrLog r = log[slot_log[pos]];
+                if (r.len != len || !bytes_equal(pool + r.off, bytes + b, len))
+                    ctr[CTR_STR_ERROR] = 2;
+                break;
+            }
+            if (k == SET_EMPTY)
+                break; // cannot happen after a successful insert pass
+            pos = (pos + 1) & mask;
+        }
+    }
+}
+
+// finalized view: ordinal -> where the key's bytes are
+__global__ void k_str_index(const StrLog *log, unsigned long long nlog, const SetSlot *probe, unsigned long long pmask, unsigned long long *str_off, unsigned *str_len) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nlog; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const long long ord = probe_lookup(probe, pmask, -1, log[i].hash);
+        if (ord >= 0) {
+            str_off[ord] = log[i].off;
+            str_len[ord] = log[i].len;
+        }
+    }
+}
+
+// ordered_set<>::map_ordinal for strings (+ the (local ordinal, shard) pair of update(return_values=True))
+__global__ void __launch_bounds__(256) k_str_map(const SetSlot *probe, unsigned long long pmask, const unsigned long long *str_off, const unsigned *str_len,
+                                                 const char *pool, long long null_ordinal, int nmaps, const long long *shard_offsets, const long long *offsets,
+                                                 const unsigned char *bytes, const uint8_t *masks, long long base, long long nrows, long long *out,
+                                                 short *out_map_index, int local_values) {
+    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += (long long)gridDim.x * blockDim.x) {
+        long long ord;
+        int shard = 0;
+        if (masks && masks[row]) {
+            ord = null_ordinal;
+        } else {
+            const long long b = offsets[row] - base;
+            const unsigned long long len = (unsigned long long)(offsets[row + 1] - offsets[row]);
+            const unsigned long long h = murmur64(bytes + b, len);
+            shard = (int)(h % (unsigned long long)nmaps);
+            ord = probe_lookup(probe, pmask, -1, h);
+            if (ord >= 0 && (str_len[ord] != len || !bytes_equal(pool + str_off[ord], bytes + b, len)))
+                ord = -1; // same hash, different string: not a member
+        }
+        if (local_values && ord >= 0)
+            ord -= shard_offsets[shard];
+        out[row] = ord;
+        if (out_map_index)
+            out_map_index[row] = (short)shard;
+    }
+}
+
+__global__ void k_str_gather(const unsigned long long *str_off, const unsigned *str_len, const unsigned *out_off, const char *pool, unsigned long long n, char *out) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const char *src = pool + str_off[i];
+        char *dst = out + out_off[i];
+        for (unsigned c = 0; c < str_len[i]; c++)
+            dst[c] = src[c];
+    }
+}
+
+// string columns staged for one call: offsets (device), bytes (device, starting at offsets[0]), masks
+struct StrInput {
+    const long long *offsets = nullptr;
+    const unsigned char *bytes = nullptr;
+    const uint8_t *masks = nullptr;
+    long long base = 0, nbytes = 0;
+};
+
+int stage_strings(b200_ctx *ctx, Slot *sl, Stager &stg, const int64_t *offsets, const uint8_t *bytes, const uint8_t *masks, int64_t nrows, int memspace, StrInput *in) {
+    long long first = 0, last = 0;
+    if (nrows) {
+        if (memspace == B200_MEM_DEVICE) {
+            B200_CUDA(cudaMemcpyAsync(&first, offsets, 8, cudaMemcpyDeviceToHost, sl->stream));
+            B200_CUDA(cudaMemcpyAsync(&last, offsets + nrows, 8, cudaMemcpyDeviceToHost, sl->stream));
+            B200_CUDA(cudaStreamSynchronize(sl->stream));
+        } else {
+            first = offsets[0], last = offsets[nrows];
+        }
+    }
+    in->base = first;
+    in->nbytes = last - first;
+    stg.plan(offsets, (size_t)(nrows + 1) * 8);
+    if (in->nbytes)
+        stg.plan(bytes + (memspace == B200_MEM_DEVICE ? 0 : first), (size_t)in->nbytes);
+    if (masks)
+        stg.plan(masks, (size_t)nrows);
+    B200_CHECK(stg.commit());
+    in->offsets = static_cast<const long long *>(stg.dev(offsets));
+    if (memspace == B200_MEM_DEVICE) {
+        in->bytes = bytes; // device: index with the absolute offsets
+        in->base = 0;
+    } else {
+        in->bytes = in->nbytes ? static_cast<const unsigned char *>(stg.dev(bytes + first)) : bytes;
+    }
+    in->masks = masks ? static_cast<const uint8_t *>(stg.dev(masks)) : nullptr;
+    (void)ctx;
+    return B200_OK;
+}
+
+int str_finalize(b200_set *s) { // caller holds s->mu
+    const bool was_dirty = s->dirty;
+    B200_CHECK(set_finalize(s));
+    if (!was_dirty && s->d_str_off)
+        return B200_OK;
+    cudaStream_t st = s->ctx->slots[0]->stream;
+    if (s->d_str_off)
+        B200_CUDA(cudaFree(s->d_str_off));
+    if (s->d_str_len)
+        B200_CUDA(cudaFree(s->d_str_len));
+    const size_t en = (size_t)(s->n_entries ? s->n_entries : 1);
+    B200_CUDA(cudaMalloc(&s->d_str_off, en * 8));
+    B200_CUDA(cudaMalloc(&s->d_str_len, en * 4));
+    B200_CUDA(cudaMemsetAsync(s->d_str_off, 0, en * 8, st));
+    B200_CUDA(cudaMemsetAsync(s->d_str_len, 0, en * 4, st));
+    unsigned long long sc[2];
+    B200_CUDA(cudaMemcpyAsync(sc, s->d_strctr, 16, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (sc[0])
+        k_str_index<<<nblocks(sc[0]), 256, 0, st>>>(s->log, sc[0], s->probe, s->probe_cap - 1, s->d_str_off, s->d_str_len);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int str_check_error(b200_set *s, cudaStream_t st) {
+    unsigned long long h[CTR_N];
+    B200_CHECK(read_ctr(s, st, h));
+    if (h[CTR_STR_ERROR]) {
+        set_error(h[CTR_STR_ERROR] == 2 ? "ordered_set_string: two different strings share one 64-bit hash (std::hash collision); refusing to merge them"
+                                        : "ordered_set_string: a string hashes to the reserved empty pattern");
+        return B200_ERR_UNSUPPORTED;
+    }
+    return B200_OK;
+}
+
+} // namespace
+} // namespace b200
+
+extern "C" {
+
+int b200_strset_create(b200_ctx *ctx, int nmaps, int64_t limit, b200_set **out) {
+    if (limit >= 0) {
+        set_error("ordered_set_string: limit is not supported");
+        return B200_ERR_UNSUPPORTED;
+    }
+    B200_CHECK(b200_set_create(ctx, B200_U64, nmaps, -1, out));
+    b200_set *s = *out;
+    s->strings = true;
+    cudaStream_t st = ctx->slots[0]->stream;
+    B200_CUDA(cudaMalloc(&s->slot_log, s->cap * sizeof(unsigned)));
+    B200_CUDA(cudaMalloc(&s->log, s->cap * sizeof(StrLog)));
+    B200_CUDA(cudaMalloc(&s->d_strctr, 16));
+    B200_CUDA(cudaMemsetAsync(s->d_strctr, 0, 16, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int b200_strset_update(b200_set *s, int slot, const int64_t *offsets, const uint8_t *bytes, const uint8_t *masks, int64_t nrows, int return_values,
+                       int64_t *out_values, int16_t *out_map_index, int memspace) {
+    if (!s || !s->strings || slot < 0 || slot >= s->ctx->nslots || nrows < 0 || (nrows && !offsets)) {
+        set_error("b200_strset_update: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    if (nrows >= (1ll << 40) - 2) {
+        set_error("b200_strset_update: more than 2^40 rows in one call");
+        return B200_ERR_UNSUPPORTED;
+    }
+    B200_CUDA(cudaSetDevice(s->ctx->device));
+    Slot *sl = s->ctx->slots[slot];
+    std::lock_guard<std::mutex> g(s->mu);
+    std::lock_guard<std::mutex> gs(sl->mu);
+    cudaStream_t st = sl->stream;
+    Stager stg{s->ctx, sl, memspace};
+    StrInput in;
+    B200_CHECK(stage_strings(s->ctx, sl, stg, offsets, bytes, masks, nrows, memspace, &in));
+    // room for the worst case of this call: every row a new key
+    {
+        uint64_t want = s->cap;
+        const uint64_t known = s->dirty ? 0 : (uint64_t)s->n_keys;
+        const uint64_t target = std::min<uint64_t>((known + (uint64_t)nrows) * 2, 1ull << 22);
+        while (want < target)
+            want <<= 1;
+        while (s->cap < want)
+            B200_CHECK(set_grow(s, st));
+        unsigned long long sc[2];
+        B200_CUDA(cudaMemcpyAsync(sc, s->d_strctr, 16, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        const uint64_t need = sc[1] + (uint64_t)in.nbytes + 16;
+        if (need > s->pool_cap) {
+            const uint64_t cap = std::max<uint64_t>(need + need / 2, 1u << 20);
+            char *np = nullptr;
+            B200_CUDA(cudaMalloc(&np, cap));
+            if (s->pool) {
+                B200_CUDA(cudaMemcpyAsync(np, s->pool, sc[1], cudaMemcpyDeviceToDevice, st));
+                B200_CUDA(cudaStreamSynchronize(st));
+                B200_CUDA(cudaFree(s->pool));
+            }
+            s->pool = np;
+            s->pool_cap = cap;
+        }
+    }
+    const unsigned long long tag_base = (unsigned long long)s->seq << 40;
+    s->seq++;
+    s->max_call_rows = std::max<int64_t>(s->max_call_rows, nrows);
+    unsigned long long h[CTR_N];
+    int redo = 0;
+    for (int attempt = 0; nrows && attempt < 64; attempt++) {
+        k_str_insert<<<nblocks((unsigned long long)nrows), 256, 0, st>>>(s->table, s->cap - 1, s->d_ctr, s->d_strctr, s->log, s->pool, s->slot_log, in.offsets, in.bytes,
+                                                                       in.masks, in.base, 0, nrows, tag_base, redo, kTagLowMask - 1);
+        B200_CUDA(cudaGetLastError());
+        B200_CHECK(read_ctr(s, st, h));
+        if (!h[CTR_OVERFLOW])
+            break;
+        unsigned long long zero = 0;
+        B200_CUDA(cudaMemcpyAsync(s->d_ctr + CTR_OVERFLOW, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
+        B200_CHECK(set_grow(s, st));
+        redo = 2; // inserts are idempotent; the nulls of this call were already counted
+    }
+    if (nrows) {
+        k_str_verify<<<nblocks((unsigned long long)nrows), 256, 0, st>>>(s->table, s->cap - 1, s->d_ctr, s->log, s->pool, s->slot_log, in.offsets, in.bytes, in.masks,
+                                                                       in.base, nrows);
+        B200_CUDA(cudaGetLastError());
+    }
+    B200_CHECK(str_check_error(s, st));
+    s->dirty = true;
+    if (return_values && nrows) {
+        B200_CHECK(str_finalize(s));
+        long long *d_vals = nullptr;
+        short *d_map = nullptr;
+        B200_CUDA(cudaMalloc(&d_vals, sizeof(long long) * nrows));
+        B200_CUDA(cudaMalloc(&d_map, sizeof(short) * nrows));
+        k_str_map<<<nblocks((unsigned long long)nrows), 256, 0, st>>>(s->probe, s->probe_cap - 1, s->d_str_off, s->d_str_len, s->pool,
+                                                                    s->null_count > 0 ? s->null_value : -1, s->nmaps, s->d_offsets, in.offsets, in.bytes, in.masks,
+                                                                    in.base, nrows, d_vals, d_map, 1);
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaMemcpyAsync(out_values, d_vals, sizeof(long long) * nrows, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaMemcpyAsync(out_map_index, d_map, sizeof(short) * nrows, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        cudaFree(d_vals);
+        cudaFree(d_map);
+    }
+    B200_CUDA(cudaStreamSynchronize(st)); // the caller's buffers are only valid during the call
+    return B200_OK;
+}
+
+/* out: nrows int64 ordinals (-1: not a member; nulls map to the null ordinal), written to host memory or, with out_is_device, to a
+ * device buffer on the slot's stream */
+int b200_strset_map_ordinal(b200_set *s, int slot, const int64_t *offsets, const uint8_t *bytes, const uint8_t *masks, int64_t nrows, int64_t *out,
+                            int memspace, int out_is_device) {
+    if (!s || !s->strings || slot < 0 || slot >= s->ctx->nslots || nrows < 0 || (nrows && (!offsets || !out))) {
+        set_error("b200_strset_map_ordinal: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    if (!nrows)
+        return B200_OK;
+    B200_CUDA(cudaSetDevice(s->ctx->device));
+    Slot *sl = s->ctx->slots[slot];
+    std::lock_guard<std::mutex> g(s->mu);
+    std::lock_guard<std::mutex> gs(sl->mu);
+    cudaStream_t st = sl->stream;
+    B200_CHECK(str_finalize(s));
+    Stager stg{s->ctx, sl, memspace};
+    StrInput in;
+    B200_CHECK(stage_strings(s->ctx, sl, stg, offsets, bytes, masks, nrows, memspace, &in));
+    long long *d_out = out_is_device ? reinterpret_cast<long long *>(out) : nullptr;
+    if (!out_is_device)
+        B200_CUDA(cudaMalloc(&d_out, sizeof(long long) * nrows));
+    k_str_map<<<nblocks((unsigned long long)nrows), 256, 0, st>>>(s->probe, s->probe_cap - 1, s->d_str_off, s->d_str_len, s->pool, s->null_count > 0 ? s->null_value : -1,
+                                                                s->nmaps, s->d_offsets, in.offsets, in.bytes, in.masks, in.base, nrows, d_out, nullptr, 0);
+    B200_CUDA(cudaGetLastError());
+    if (!out_is_device)
+        B200_CUDA(cudaMemcpyAsync(out, d_out, sizeof(long long) * nrows, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (!out_is_device)
+        cudaFree(d_out);
+    return B200_OK;
+}
+
+/* key_array(): first the byte count, then offsets (int64[count + 1]) + bytes in ordinal order; the null slot is an empty string */
+int b200_strset_key_bytes(b200_set *s, int64_t *nbytes_out) {
+    if (!s || !s->strings || !nbytes_out) {
+        set_error("b200_strset_key_bytes: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(s->ctx->device));
+    std::lock_guard<std::mutex> g(s->mu);
+    B200_CHECK(str_finalize(s));
+    std::vector<unsigned> len(s->n_entries);
+    if (s->n_entries)
+        B200_CUDA(cudaMemcpy(len.data(), s->d_str_len, s->n_entries * 4, cudaMemcpyDeviceToHost));
+    int64_t total = 0;
+    for (unsigned v : len)
+        total += v;
+    *nbytes_out = total;
+    return B200_OK;
+}
+
+int b200_strset_key_array(b200_set *s, int64_t *offsets_out, uint8_t *bytes_out) {
+    if (!s || !s->strings || !offsets_out) {
+        set_error("b200_strset_key_array: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(s->ctx->device));
+    std::lock_guard<std::mutex> g(s->mu);
+    B200_CHECK(str_finalize(s));
+    const uint64_t n = s->n_entries;
+    std::vector<unsigned> len(n), off(n + 1, 0);
+    if (n)
+        B200_CUDA(cudaMemcpy(len.data(), s->d_str_len, n * 4, cudaMemcpyDeviceToHost));
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        offsets_out[i] = (int64_t)total;
+        off[i] = (unsigned)total;
+        total += len[i];
+    }
+    offsets_out[n] = (int64_t)total;
+    if (total >= (1ull << 32)) {
+        set_error("ordered_set_string.key_array: more than 4 GB of keys");
+        return B200_ERR_UNSUPPORTED;
+    }
+    if (!total || !bytes_out)
+        return B200_OK;
+    cudaStream_t st = s->ctx->slots[0]->stream;
+    unsigned *d_off = nullptr;
+    char *d_bytes = nullptr;
+    B200_CUDA(cudaMalloc(&d_off, (n + 1) * 4));
+    B200_CUDA(cudaMalloc(&d_bytes, total));
+    B200_CUDA(cudaMemcpyAsync(d_off, off.data(), (n + 1) * 4, cudaMemcpyHostToDevice, st));
+    k_str_gather<<<nblocks(n), 256, 0, st>>>(s->d_str_off, s->d_str_len, d_off, s->pool, n, d_bytes);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaMemcpyAsync(bytes_out, d_bytes, total, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_off);
+    cudaFree(d_bytes);
+    return B200_OK;
+}
 
 } // extern "C"

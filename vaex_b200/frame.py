@@ -19,6 +19,8 @@ def _is_device(x):
 
 
 def _dtype_of(ar):
+    if _hash.is_string_column(ar):
+        return np.dtype("O")
     if getattr(ar, "device_virtual", False):  # device-evaluated virtual column (hash.CombinedCodes)
         return ar.dtype
     if _is_device(ar):
@@ -395,7 +397,11 @@ class GroupBy:
             return out
         for name, hm in zip(self.by, self.hash_maps):
             dtype = _dtype_of(df.columns[name])
-            if self.fused:
+            if hm.is_string:
+                cname = f"_ordinal_values({name})"
+                columns[cname] = _hash.StringCodes(df.columns[name], hm)
+                specs.append({"binner-type": "ordinal", "expression": cname, "dtype": "<i8", "count": len(hm), "minimum": 0, "invert": False})
+            elif self.fused:
                 specs.append({"binner-type": "hash", "expression": name, "dtype": dtype.str, "hash_map_unique": hm})
             else:
                 codes = hm.map(df.columns[name])

@@ -7,8 +7,21 @@ import numpy as np
 from . import superutils
 
 
+def is_string_column(ar):
+    """pyarrow string / large_string arrays, numpy object / unicode arrays"""
+    try:
+        import pyarrow as pa
+        if isinstance(ar, (pa.Array, pa.ChunkedArray)):
+            return pa.types.is_string(ar.type) or pa.types.is_large_string(ar.type)
+    except ImportError:  # pragma: no cover
+        pass
+    return isinstance(ar, np.ndarray) and ar.dtype.kind in "OU"
+
+
 def ordered_set_type_from_dtype(dtype):
     dtype = np.dtype(dtype)
+    if dtype.kind in "OU":  # vaex.hash: string keys -> ordered_set_string (src/hash_string.hpp)
+        return superutils.ordered_set_string
     if dtype.kind in "mM":
         dtype = np.dtype("int64")
     name = "ordered_set_" + dtype.newbyteorder("=").name
@@ -29,8 +42,14 @@ class HashMapUnique:
         else:
             self._internal = _internal
 
+    @property
+    def is_string(self):
+        return self.dtype.kind in "OU"
+
     def flatten(self):
         # vaex/hash.py:75-80: rebuild a 1-shard set from key_array() so ordinals become global
+        if self.is_string:  # the device string set already answers map_ordinal with GLOBAL ordinals (local + offsets[shard])
+            return self
         keys = self._internal.key_array()
         m = type(self._internal)(keys, self.null_index, self.nan_count, self.null_count, self.fingerprint)
         return HashMapUnique(self.dtype, _internal=m)
@@ -55,6 +74,8 @@ class HashMapUnique:
     def add(self, ar, return_inverse=False):
         # vaex/hash.py:152-171
         chunk_size = 1024 * 1024
+        if self.is_string:
+            return self._internal.update(ar, -1, chunk_size=chunk_size, bucket_size=chunk_size * 4, return_values=return_inverse)
         is_device = hasattr(ar, "__cuda_array_interface__") and not isinstance(ar, np.ndarray)
         if not is_device and np.ma.isMaskedArray(ar):
             mask = np.ma.getmaskarray(ar)
@@ -73,6 +94,8 @@ class HashMapUnique:
     def keys(self, mask=True):
         # vaex/hash.py:179-191
         ar = self._internal.key_array()
+        if self.is_string:
+            return np.array(ar.to_pylist(), dtype=object)
         if self.dtype_item.kind in "mM":
             ar = ar.view(self.dtype_item)
         if mask and self.has_null:
@@ -83,6 +106,9 @@ class HashMapUnique:
 
     def map(self, keys, check_missing=False):
         """Map key values to unique integers (vaex/hash.py:193-214)."""
+        if self.is_string:
+            indices = self._internal.map_ordinal(keys)
+            return np.ma.array(indices, mask=indices == -1) if check_missing else indices
         masked = isinstance(keys, np.ndarray) and np.ma.isMaskedArray(keys)
         data = np.ascontiguousarray(keys.data) if masked else keys
         indices = self._internal.map_ordinal(data)
@@ -115,6 +141,11 @@ class HashMapUnique:
         return self._internal.fingerprint
 
     def sorted(self, ascending=True, return_keys=False):
+        if self.is_string:
+            raise NotImplementedError("sorted string key sets are not supported: sort the result by key instead")
+        return self._sorted(ascending, return_keys)
+
+    def _sorted(self, ascending=True, return_keys=False):
         # vaex/hash.py:246-268 — arrow sorts nulls last; NaN sorts after every number
         keys = self.keys(mask=False)
         has_null = self.has_null
@@ -233,3 +264,22 @@ class CombinedCodes:
             out.append(left // m)
             left = left % m
         return out
+
+
+class StringCodes:
+    """``_ordinal_values(key, hash_map_unique)`` for a STRING key column as a device-evaluated int64 column: every chunk's strings
+    are probed against the device string set on the worker's slot (vaex/functions.py:2454-2463 + HashMapUnique.map,
+    vaex/hash.py:193-214); the codes feed a BinnerOrdinal exactly like the reference's pass 2 does (vaex/groupby.py:303-317)."""
+
+    device_virtual = True
+
+    def __init__(self, column, hash_map):
+        self.columns = [column]  # host strings: the executor feeds host chunks
+        self.hash_map = hash_map
+        self.dtype = np.dtype("int64")
+
+    def __len__(self):
+        return len(self.columns[0])
+
+    def chunk(self, thread_index, i1, i2):
+        return self.hash_map._internal.map_ordinal(self.columns[0][i1:i2], slot=thread_index, device=True)

@@ -433,9 +433,92 @@ for _name in _DT:
         for _name2 in _DT:
             _make("AggFirst_" + _name + "_" + _name2 + ("_non_native" if _nn else ""), Aggregator, _op=_lib.AGG_FIRST, _dtype2=_name2, **_common)
 
-# names the B200 path does not provide: list / string / object aggregators (incl. AggNUnique_string) and BinnerCombined
-# (out of scope).  Accessing them raises instead of silently doing something else.
-_UNSUPPORTED_PREFIXES = ("AggNUnique_", "AggList_", "AggCount_string", "AggCount_object", "BinnerCombined")
+
+# ---- string aggregators (src/agg_count.cpp:70-195 AggCount_string, src/agg_nunique_string.cpp AggNUnique_string) ----------------
+class AggCount_string(Aggregator):
+    """count(string column) = rows whose string is not null, per cell (src/agg_count.cpp:120-160).  The string column is reduced to
+    its validity bytes on the host (one byte per row, the arrow bitmap unpacked); the device counts them with the ordinary
+    AggCount kernel, the validity doubling as the data mask."""
+    _dtype, _code, _non_native, _itemsize, _op = "uint8", _lib.DTYPE_CODE["uint8"], False, 1, _lib.AGG_COUNT
+
+    def set_data(self, thread, ar, index=0):
+        from .superutils import string_buffers
+        offsets, _, mask = string_buffers(ar)
+        n = len(offsets) - 1
+        valid = np.ones(n, np.uint8) if mask is None else (1 - mask).astype(np.uint8)
+        self._valid = getattr(self, "_valid", {})
+        self._valid[int(thread)] = valid
+        super().set_data(thread, valid, 0)
+        self._string_mask_user = getattr(self, "_string_mask_user", {})
+        self._apply_mask(int(thread))
+
+    def _apply_mask(self, thread):
+        user = self._string_mask_user.get(thread)
+        valid = self._valid.get(thread)
+        if valid is None:
+            return
+        m = valid if user is None else (valid & (np.asarray(user) != 0).astype(np.uint8))
+        super().set_data_mask(thread, m)
+
+    def set_data_mask(self, thread, ar):
+        self._string_mask_user = getattr(self, "_string_mask_user", {})
+        self._string_mask_user[int(thread)] = ar
+        self._apply_mask(int(thread))
+
+    def clear_data_mask(self, thread):
+        self._string_mask_user = getattr(self, "_string_mask_user", {})
+        self._string_mask_user.pop(int(thread), None)
+        self._apply_mask(int(thread))
+
+
+class AggNUnique_string(_AggNUnique):
+    """nunique(string column) per cell (src/agg_nunique_string.cpp:10-95: a counter<string> per cell).  Here the strings are first
+    encoded by ONE device ordered_set_string (nmaps = 1: a key's ordinal never changes once assigned) and the per-cell distinct
+    count runs over the int64 ordinals with the numeric AggNUnique kernel — equal strings have equal ordinals and different
+    strings different ones (the string set verifies the bytes behind every hash), so the counts are the reference's."""
+    _dtype, _code, _non_native, _itemsize = "int64", _lib.DTYPE_CODE["int64"], False, 8
+
+    def __init__(self, grid, grids, threads, dropmissing=False, dropnan=False):
+        super().__init__(grid, grids, threads, dropmissing, dropnan)
+        from .superutils import ordered_set_string
+        self._strings = ordered_set_string(1)
+        self._codes = {}
+
+    def set_data(self, thread, ar, index=0):
+        from .superutils import string_buffers
+        thread = int(thread)
+        _, _, mask = string_buffers(ar)
+        self._strings.update(ar)
+        codes = self._strings.map_ordinal(ar, slot=thread, device=True)
+        self._codes[thread] = codes
+        super().set_data(thread, codes, 0)
+        n = len(codes)
+        self._valid = getattr(self, "_valid", {})
+        self._valid[thread] = np.ones(n, np.uint8) if mask is None else (1 - mask).astype(np.uint8)
+        self._apply_mask(thread)
+
+    # the task part sets / clears the data mask AFTER set_data (vaex/cpu.py:765-784): the strings' own validity has to survive that
+    def _apply_mask(self, thread):
+        valid = getattr(self, "_valid", {}).get(thread)
+        if valid is None:
+            return
+        user = getattr(self, "_user_mask", {}).get(thread)
+        m = valid if user is None else (valid & (np.asarray(user) != 0).astype(np.uint8))
+        super().set_data_mask(thread, m)  # NUNIQUE: mask = 0 marks a null row (include/b200agg.h)
+
+    def set_data_mask(self, thread, ar):
+        self._user_mask = getattr(self, "_user_mask", {})
+        self._user_mask[int(thread)] = ar
+        self._apply_mask(int(thread))
+
+    def clear_data_mask(self, thread):
+        getattr(self, "_user_mask", {}).pop(int(thread), None)
+        self._apply_mask(int(thread))
+
+
+# names the B200 path does not provide: list / object aggregators and BinnerCombined's pybind name for unsupported dtypes.
+# Accessing them raises instead of silently doing something else.
+_UNSUPPORTED_PREFIXES = ("AggCount_object",)
 
 
 def __getattr__(name):

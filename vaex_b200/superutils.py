@@ -269,3 +269,140 @@ for _name in _lib.DTYPES:
     _cls = type("counter_" + _name, (_Counter,), dict(_dtype=_name, _code=_lib.DTYPE_CODE[_name]))
     _cls.__module__ = __name__
     globals()["counter_" + _name] = _cls
+
+
+# ---- string keys (src/hash_string.hpp, bound in src/hash_string.cpp:86-99 as ordered_set_string) ------------------------------------
+def string_buffers(values):
+    """strings -> (int64 offsets[n + 1], uint8 bytes, uint8 null mask or None): the arrow large_string layout the reference's
+    StringList64 uses.  Accepts pyarrow string / large_string arrays (zero copy for large_string), numpy object / str arrays and
+    lists of str / None."""
+    try:
+        import pyarrow as pa
+    except ImportError:  # pragma: no cover
+        pa = None
+    if pa is not None and isinstance(values, pa.ChunkedArray):
+        values = values.combine_chunks()
+    if pa is not None and isinstance(values, pa.Array):
+        if pa.types.is_string(values.type):
+            values = values.cast(pa.large_string())
+        if not pa.types.is_large_string(values.type):
+            raise TypeError(f"expected a string array, got {values.type}")
+        n = len(values)
+        validity, off_buf, data_buf = values.buffers()
+        offsets = np.frombuffer(off_buf, dtype=np.int64, count=n + 1, offset=values.offset * 8)
+        data = np.frombuffer(data_buf, dtype=np.uint8) if data_buf is not None else np.zeros(0, np.uint8)
+        mask = None
+        if values.null_count:
+            bits = np.unpackbits(np.frombuffer(validity, dtype=np.uint8), bitorder="little")[values.offset:values.offset + n]
+            mask = np.ascontiguousarray(1 - bits).astype(np.uint8)
+        return offsets, data, mask
+    seq = values.tolist() if isinstance(values, np.ndarray) else list(values)
+    enc = [(s.encode("utf8") if s is not None else b"") for s in seq]
+    offsets = np.zeros(len(enc) + 1, np.int64)
+    if enc:
+        offsets[1:] = np.cumsum([len(e) for e in enc])
+    data = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if offsets[-1] else np.zeros(0, np.uint8)
+    mask = np.array([s is None for s in seq], np.uint8)
+    return offsets, data, (mask if mask.any() else None)
+
+
+class ordered_set_string:
+    """``vaex.superutils.ordered_set_string(nmaps, limit=-1)``: the ordinal encoder for string keys, on the device.
+    update / map_ordinal / key_array / keys / offsets / len / null_count / has_null / null_index follow the reference
+    (src/hash_string.hpp); ``limit``, ``isin``, ``merge`` and ``flatten_values`` are not provided."""
+
+    def __init__(self, nmaps=1, limit=-1):
+        self._ctx = _lib.context()
+        self._h = C.c_void_p()
+        self.nmaps = int(nmaps)
+        self.fingerprint = ""
+        self.sealed = False
+        _lib.check(_lib.lib().b200_strset_create(self._ctx._h, self.nmaps, int(limit), C.byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().b200_set_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    @staticmethod
+    def _np_dtype():
+        return np.dtype("O")
+
+    def update(self, values, start_index=0, chunk_size=1024 * 128, bucket_size=1024 * 128, return_values=False, slot=0):
+        if self.sealed:
+            raise RuntimeError("cannot add to sealed hashmap")
+        if bucket_size < chunk_size:
+            raise RuntimeError("bucket size should be larger than chunk_size")
+        offsets, data, mask = string_buffers(values)
+        n = len(offsets) - 1
+        vals = np.empty(n if return_values else 1, np.int64)
+        mi = np.empty(n if return_values else 1, np.int16)
+        _lib.check(_lib.lib().b200_strset_update(self._h, self._ctx.slot(slot), offsets.ctypes.data, data.ctypes.data if data.size else None,
+                                                 None if mask is None else mask.ctypes.data, n, int(bool(return_values)), vals.ctypes.data, mi.ctypes.data, _lib.MEM_HOST))
+        return (vals, mi) if return_values else None
+
+    def map_ordinal(self, values, slot=0, device=False):
+        """global ordinals, -1 for strings that are not members; device=True returns a device array (for the fused groupby pass)"""
+        offsets, data, mask = string_buffers(values)
+        n = len(offsets) - 1
+        args = (offsets.ctypes.data, data.ctypes.data if data.size else None, None if mask is None else mask.ctypes.data, n)
+        if device:
+            import torch
+            from .expression import DeviceArray
+            buf = torch.empty(max(n, 1), dtype=torch.int64, device=f"cuda:{self._ctx.device}")
+            _lib.check(_lib.lib().b200_strset_map_ordinal(self._h, self._ctx.slot(slot), *args, buf.data_ptr(), _lib.MEM_HOST, 1))
+            return DeviceArray(buf.data_ptr(), n, np.int64, keep=buf)
+        out = np.empty(n, np.int64)
+        _lib.check(_lib.lib().b200_strset_map_ordinal(self._h, self._ctx.slot(slot), *args, out.ctypes.data, _lib.MEM_HOST, 0))
+        return out
+
+    def _key_buffers(self):
+        n = len(self)
+        nbytes = C.c_int64(0)
+        _lib.check(_lib.lib().b200_strset_key_bytes(self._h, C.byref(nbytes)))
+        offsets = np.zeros(n + 1, np.int64)
+        data = np.zeros(max(nbytes.value, 1), np.uint8)
+        _lib.check(_lib.lib().b200_strset_key_array(self._h, offsets.ctypes.data, data.ctypes.data))
+        return offsets, data[:nbytes.value]
+
+    def key_array(self):
+        """the keys in ordinal order as a pyarrow large_string array (the reference hands out a StringList64); the null slot is null"""
+        import pyarrow as pa
+        offsets, data = self._key_buffers()
+        n = len(offsets) - 1
+        validity = None
+        if self.null_count:
+            bits = np.ones(n, np.uint8)
+            bits[self.null_index] = 0
+            validity = pa.py_buffer(np.packbits(bits, bitorder="little").tobytes())
+        return pa.Array.from_buffers(pa.large_string(), n, [validity, pa.py_buffer(offsets.tobytes()), pa.py_buffer(data.tobytes())], null_count=1 if self.null_count else 0)
+
+    def keys(self):
+        return self.key_array().to_pylist()
+
+    def seal(self):
+        self.sealed = True
+
+    def __len__(self):
+        return int(_lib.lib().b200_set_count(self._h))
+
+    count = property(lambda self: len(self))
+    nan_count = property(lambda self: 0)
+    null_count = property(lambda self: int(_lib.lib().b200_set_null_count(self._h)))
+    has_nan = property(lambda self: False)
+    has_null = property(lambda self: self.null_count > 0)
+    nan_index = property(lambda self: -1)
+    null_index = property(lambda self: int(_lib.lib().b200_set_null_index(self._h)))  # 0x7fffffff until a null was seen
+
+    @property
+    def offset(self):
+        return int(self.null_count > 0)
+
+    def offsets(self):
+        out = np.zeros(self.nmaps, np.int64)
+        _lib.check(_lib.lib().b200_set_offsets(self._h, out.ctypes.data))
+        return out.tolist()

@@ -112,8 +112,8 @@ class TaskPartAggregation(TaskPart):
 
         def split(block):
             """-> (data, numpy-style mask or None); datetimes travel as integers (vaex/cpu.py:692-694)."""
-            if _is_device(block):
-                return block, None
+            if _is_device(block) or _hash.is_string_column(block):
+                return block, None  # string columns go to AggCount_string / AggNUnique_string as they are
             if np.ma.isMaskedArray(block):
                 return np.ascontiguousarray(block.data), np.ma.getmaskarray(block)
             block = np.asarray(block)
