@@ -75,7 +75,9 @@ typedef enum {
     B200_AGG_FIRST, B200_AGG_LAST,
     B200_AGG_NUNIQUE /* AggNUnique_<T>(grid, grids, threads, dropmissing, dropnan) (src/agg_nunique.cpp): `moment` bit 0 = dropmissing,
                         bit 1 = dropnan.  b200_agg_input: `mask` = validity (1 = value present, 0 = null row: the reference's
-                        data mask), `order` = selection mask (uint8, 1 = the row takes part: set_selection_mask); both nullable */
+                        data mask), `order` = selection mask (uint8, 1 = the row takes part: set_selection_mask); both nullable */,
+    B200_AGG_LIST /* AggList_<T>(grid, grids, threads, dropnan, dropnull) (src/agg_list.cpp:5-127): `moment` bit 0 = dropnan, bit 1 =
+                     dropnull; read with b200_agg_list_finish / b200_agg_list_read, not b200_agg_read */
 } b200_agg_op;
 
 /* where the column pointers of a call live.  MIXED: every pointer is classified on its own (cudaPointerGetAttributes);
@@ -154,6 +156,11 @@ int b200_agg_device_dtype(const b200_agg *agg);
 /* D2H of the finished grid in result dtype; `cell_masked` (nullable) is filled for FIRST/LAST (1 = empty cell) */
 int b200_agg_read(b200_agg *agg, void *values_out, uint8_t *cell_masked_out);
 int b200_agg_merge(b200_agg *agg, b200_agg *const *others, int nothers);
+/* AggList results (src/agg_list.cpp:47-83 get_result): per cell the values in arrival order, then one NaN per NaN value seen (unless
+ * dropnan), then one slot per null row (unless dropnull).  finish: sorts the appended records, returns the flat length; read: int64
+ * offsets[cells + 1] and `total` values of the aggregator's dtype.  merge() is a no-op like the reference's (:46). */
+int b200_agg_list_finish(b200_agg *agg, int64_t *total_out);
+int b200_agg_list_read(b200_agg *agg, int64_t *offsets_out, void *values_out);
 /* load a full grid (result dtype, `cells` long) — TaskPartAggregation initial_values (vaex/cpu.py:654-658) */
 int b200_agg_write(b200_agg *agg, const void *values);
 

@@ -121,3 +121,84 @@ def test_concurrent_process_on_one_shared_part(oracle):
     want = oracle.binby([oracle.scalar(x, -3, 3, 32)], [oracle.agg("count"), oracle.agg("sum", v), oracle.agg("max", v)], n)
     assert np.array_equal(count, want[0][2:-1]) and np.array_equal(total, want[1][2:-1]) and np.array_equal(vmax, want[2])
     assert part.memory_usage() > 0
+
+
+def test_binner_combined_and_map_many(oracle):
+    """BinnerCombined (src/binner_combined.cpp:25-29: member indices composed with strides 1, shape_0, ...) and hash_map::map_many
+    (src/hash_primitives.hpp:567-590: global ordinals as int64, NaN -> NaN ordinal, absent -> -1)"""
+    import pickle
+    from vaex_b200 import superagg, superutils
+    rng = np.random.default_rng(12)
+    n = 20_000
+    x, y = rng.standard_normal(n), rng.standard_normal(n).astype("f4")
+    z = rng.integers(0, 4, n).astype("i4")
+    bx, by = superagg.BinnerScalar_float64(1, "x", -3, 3, 10), superagg.BinnerScalar_float32(1, "y", -2, 2, 5)
+    bz = superagg.BinnerOrdinal_int32(1, "z", 4, 0, False, False)
+    comb = superagg.BinnerCombined(1, [bx, by])
+    assert len(comb) == len(by) and comb.strides == [1, len(bx)] and len(comb.copy().binners) == 2
+    assert [type(b).__name__ for b in pickle.loads(pickle.dumps(comb)).binners] == ["BinnerScalar_float64", "BinnerScalar_float32"]
+    grid = superagg.Grid([comb, bz])
+    assert grid.shapes == [13, 8, 6] and grid.strides == [1, 13, 104]
+    agg = superagg.AggCount_int64(grid, 1, 1)
+    for b, a in ((bx, x), (by, y), (bz, z)):
+        b.set_data(0, a)
+    grid.bin(0, [agg], n)
+    want = oracle.binby([oracle.scalar(x, -3, 3, 10), oracle.scalar(y, -2, 2, 5), oracle.ordinal(z, 4)], [oracle.agg("count")])[0]
+    assert np.array_equal(agg.get_result(), want)
+    keys = rng.integers(0, 50, n).astype("f8") * 0.5
+    keys[::17] = np.nan
+    s = superutils.ordered_set_float64(3)
+    s.update(keys[: n // 2], -1)
+    so = oracle.OrderedSet("float64", 3)
+    so.update(keys[: n // 2], None, -1, False)
+    probe = np.concatenate([keys, [1e9, -7.25]])
+    out = np.full(100, -99, np.int64)
+    s.map_many(probe, len(probe) - 100, 100, out)
+    assert np.array_equal(out, so.map_ordinal(probe)[-100:].astype(np.int64))
+
+
+def test_agg_list_matches_the_reference_semantics():
+    """AggList_<dtype>_int64 (src/agg_list.cpp:84-113 aggregate, :47-83 get_result): per cell the non-NaN values of the valid rows in
+    arrival order, then one NaN per NaN value (unless dropnan), then one slot per null row (unless dropnull); several calls append."""
+    from vaex_b200 import superagg
+    rng = np.random.default_rng(21)
+    n = 30_000
+    x = rng.integers(0, 6, n).astype("i4")
+    y = rng.standard_normal(n)
+    v = rng.standard_normal(n).astype("f4")
+    v[rng.random(n) < 0.1] = np.nan
+    valid = (rng.random(n) < 0.85).astype("u1")
+    for dropnan, dropnull in ((False, False), (True, False), (False, True), (True, True)):
+        bx = superagg.BinnerOrdinal_int32(1, "x", 6, 0, False, False)
+        by = superagg.BinnerScalar_float64(1, "y", -1, 1, 3)
+        grid = superagg.Grid([bx, by])
+        agg = superagg.AggList_float32_int64(grid, 1, 1, dropnan, dropnull)
+        cells = len(grid)
+        want = [[] for _ in range(cells)]
+        nans, nulls = np.zeros(cells, int), np.zeros(cells, int)
+        for i1, i2 in ((0, 9_001), (9_001, n)):  # two calls: the lists keep growing in call order
+            bx.set_data(0, x[i1:i2])
+            by.set_data(0, y[i1:i2])
+            agg.set_data(0, v[i1:i2], 0)
+            agg.set_data_mask(0, valid[i1:i2])
+            grid.bin(0, [agg], i2 - i1)
+        for i in range(n):
+            s = (y[i] + 1) * 0.5
+            cy = 1 if s < 0 else 5 if s >= 1 else int(s * 3) + 2
+            c = int(x[i]) + 8 * cy
+            if valid[i] == 1:
+                if v[i] == v[i]:
+                    want[c].append(v[i])
+                elif not dropnan:
+                    nans[c] += 1
+            elif not dropnull:
+                nulls[c] += 1
+        offsets, values = agg.result_arrays()
+        assert len(offsets) == cells + 1 and offsets[-1] == len(values)
+        for c in range(cells):
+            got = values[offsets[c]:offsets[c + 1]]
+            k = len(want[c])
+            assert len(got) == k + nans[c] + nulls[c], (c, dropnan, dropnull)
+            assert np.array_equal(got[:k], np.array(want[c], "f4"))
+            assert np.isnan(got[k:k + nans[c]]).all()
+        assert agg.get_result().type.value_type == "float" and len(agg.get_result()) == cells

@@ -36,8 +36,10 @@ def test_descriptor_specs_match_vaex_encoding():
     assert agg.nunique("x").encode() == {"aggregation": "nunique", "expressions": ["x"]}
     spec = {"aggregation": "nunique", "expressions": ["x"], "dropmissing": True, "dropnan": True}
     assert agg.nunique("x", dropna=True).encode() == spec and agg.from_spec(spec).encode() == spec
+    spec = {"aggregation": "list", "expressions": ["x"], "parameters": [True, False]}  # vaex/agg.py:240-252: agg_args travel as "parameters"
+    assert agg.from_spec(spec).encode() == spec and agg.list("x", dropnan=True).encode() == spec
     with pytest.raises(ValueError):
-        agg.from_spec({"aggregation": "list", "expressions": ["x"]})
+        agg.from_spec({"aggregation": "describe", "expressions": ["x"]})
 
 
 def test_prepare_types_and_class_lookup():

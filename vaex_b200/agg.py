@@ -14,7 +14,7 @@ import numpy as np
 
 from . import superagg
 
-_min, _max = min, max
+_min, _max, _list = min, max, list  # the module defines its own min / max / list, like vaex.agg does
 
 
 def _upcast(dtype):
@@ -62,7 +62,7 @@ class AggregatorDescriptorBasic(AggregatorDescriptor):
     def __init__(self, name, expressions, short_name, agg_args=(), selection=None, edges=False):
         self.name = name
         self.short_name = short_name
-        self.agg_args = list(agg_args)
+        self.agg_args = _list(agg_args)
         self.edges = edges
         self.selection = selection
         self.expressions = [str(k) for k in expressions if k is not None]
@@ -73,7 +73,7 @@ class AggregatorDescriptorBasic(AggregatorDescriptor):
         # identical keys to vaex/agg.py:240-252
         spec = {"aggregation": self.short_name}
         if self.expressions:
-            spec["expressions"] = list(self.expressions)
+            spec["expressions"] = _list(self.expressions)
         if self.selection is not None:
             spec["selection"] = self.selection
         if self.edges:
@@ -102,7 +102,7 @@ class AggregatorDescriptorBasic(AggregatorDescriptor):
 
     def _create_operation(self, grid, nthreads):
         # vaex/agg.py:278-321
-        if self.name == "AggFirst":
+        if self.name in ("AggFirst", "AggList"):
             if len(self.dtypes_in) == 1:
                 agg_op_type = find_type_from_dtype(superagg, self.name + "_", self.dtypes_in[0], np.dtype("int64"))
             else:
@@ -118,6 +118,11 @@ class AggregatorDescriptorBasic(AggregatorDescriptor):
         if ncells >= 1e6:
             grids = _min(8, nthreads)
         grids = _max(grids, 1)
+        if self.short_name == "list":  # "cannot predict memory usage", grids = 1 (vaex/agg.py:306-309)
+            import sys
+            agg_op = agg_op_type(grid, 1, nthreads, *self.agg_args)
+            self.predicted_memory_usage = sys.getsizeof(agg_op)
+            return agg_op
         # memory pre-declaration (vaex/agg.py:309-318): bytes_per_cell * cells * grids is declared before the aggregator exists and
         # must equal what the object then reports
         import sys
@@ -132,6 +137,8 @@ class AggregatorDescriptorBasic(AggregatorDescriptor):
     def get_result(self, agg_operation):
         # vaex/agg.py:323-335: drop the edge cells unless edges=True (scalar [2:-1], ordinal [0:-2])
         grid = agg_operation.get_result()
+        if self.short_name == "list":
+            return grid  # one list per cell of the FULL grid (edge cells included), flat order, first binner fastest
         if not self.edges:
             def binner2slice(binner):
                 name = type(binner).__name__
@@ -280,7 +287,17 @@ def from_spec(spec):
         return f(exprs[0], exprs[1] if len(exprs) > 1 else None, **kw)
     if name == "nunique":
         return nunique(exprs[0], dropnan=spec.get("dropnan", False), dropmissing=spec.get("dropmissing", False), **kw)
+    if name == "list":
+        params = spec.get("parameters", [False, False])
+        return list(exprs[0], dropnan=params[0], dropmissing=params[1], **kw)
     raise ValueError(f"aggregation {name!r} is not on the B200 hot path")
+
+
+def list(expression, selection=None, dropna=False, dropnan=False, dropmissing=False, edges=False):
+    """Aggregator that returns the list of values per bin (vaex/agg.py:654-674 -> AggList_<dtype>_int64, src/agg_list.cpp)."""
+    if dropna:
+        dropnan = dropmissing = True
+    return AggregatorDescriptorBasic("AggList", [expression], "list", agg_args=[dropnan, dropmissing], selection=selection, edges=edges)
 
 
 def nunique(expression, dropna=False, dropnan=False, dropmissing=False, selection=None, edges=False):
@@ -291,4 +308,4 @@ def nunique(expression, dropna=False, dropnan=False, dropmissing=False, selectio
     return AggregatorDescriptorNUnique("AggNUnique", [expression], "nunique", dropmissing, dropnan, selection=selection, edges=edges)
 
 
-aggregates = {f.__name__: f for f in (count, sum, min, max, first, last, mean, var, std, skew, kurtosis, nunique)}
+aggregates = {f.__name__: f for f in (count, sum, min, max, first, last, mean, var, std, skew, kurtosis, nunique, list)}

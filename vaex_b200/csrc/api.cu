@@ -152,6 +152,12 @@ static int64_t narrow_limit(int dtype, bool mx) {
 }
 
 static int agg_fill(b200_agg *a, cudaStream_t st) {
+    if (a->op == B200_AGG_LIST) { // initial_fill: empty lists
+        std::lock_guard<std::mutex> g(a->nmu);
+        a->list_n = a->list_total = 0;
+        a->list_sorted = false;
+        return B200_OK;
+    }
     if (a->op == B200_AGG_NUNIQUE) {
         B200_CUDA(cudaMemsetAsync(a->grid, 0, (a->cells ? a->cells : 1) * 8 * 3, st));
         if (a->ntable)
@@ -210,6 +216,10 @@ static int agg_fill(b200_agg *a, cudaStream_t st) {
 }
 
 } // namespace b200
+
+namespace b200 {
+int bin_list(b200_ctx *ctx, Slot *sl, b200_agg *a, const DevBinner *db, int nbinners, const void *data, const uint8_t *mask, int64_t nrows, bool vec); // list.cu
+}
 
 using namespace b200;
 
@@ -362,7 +372,7 @@ int b200_ctx_path_stats(b200_ctx *ctx, int slot, uint64_t out[6]) {
 
 // ---- aggregators -----------------------------------------------------------------------------------
 int b200_agg_create(b200_ctx *ctx, int op, int dtype, int dtype2, int byteswap, uint32_t moment, uint64_t cells, b200_agg **out) {
-    if (!ctx || !out || op < B200_AGG_COUNT || op > B200_AGG_NUNIQUE || dtype < 0 || dtype >= B200_NDTYPE || dtype2 < 0 || dtype2 >= B200_NDTYPE) {
+    if (!ctx || !out || op < B200_AGG_COUNT || op > B200_AGG_LIST || dtype < 0 || dtype >= B200_NDTYPE || dtype2 < 0 || dtype2 >= B200_NDTYPE) {
         set_error("b200_agg_create: invalid argument");
         return B200_ERR_INVALID;
     }
@@ -378,13 +388,14 @@ int b200_agg_create(b200_ctx *ctx, int op, int dtype, int dtype2, int byteswap, 
     switch (op) {
     case B200_AGG_COUNT:
     case B200_AGG_NUNIQUE: a->cell_dtype = B200_I64; break;
+    case B200_AGG_LIST: a->cell_dtype = B200_U8; break; // no cell-shaped state: records are appended (list.cu)
     case B200_AGG_SUM:
     case B200_AGG_SUM_MOMENT: a->cell_dtype = dtype_upcast(dtype); break;
     case B200_AGG_MIN:
     case B200_AGG_MAX: a->cell_dtype = dtype_minmax_cell(dtype); break;
     default: a->cell_dtype = dtype; break;
     }
-    const size_t n = cells ? cells : 1;
+    const size_t n = op == B200_AGG_LIST ? 16 : (cells ? cells : 1);
     cudaError_t e = cudaMalloc(&a->grid, n * dtype_size(a->cell_dtype) * (op == B200_AGG_NUNIQUE ? 3 : 1));
     if (e == cudaSuccess && op == B200_AGG_NUNIQUE)
         e = cudaMalloc((void **)&a->ntotal, 8);
@@ -428,6 +439,9 @@ int b200_agg_destroy(b200_agg *a) {
     cudaFree(a->cell_masked);
     cudaFree(a->ntable);
     cudaFree(a->ntotal);
+    cudaFree(a->list_keys);
+    cudaFree(a->list_vals);
+    cudaFree(a->list_counts);
     if (a->chain)
         cudaEventDestroy(a->chain);
     delete a;
@@ -463,8 +477,8 @@ int b200_agg_read_on(b200_agg *a, int slot, void *values_out) {
         set_error("b200_agg_read_on: invalid argument");
         return B200_ERR_INVALID;
     }
-    if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST || a->op == B200_AGG_NUNIQUE) {
-        set_error("b200_agg_read_on: not available for first/last/nunique");
+    if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST || a->op == B200_AGG_NUNIQUE || a->op == B200_AGG_LIST) {
+        set_error("b200_agg_read_on: not available for first/last/nunique/list");
         return B200_ERR_UNSUPPORTED;
     }
     B200_CUDA(cudaSetDevice(a->ctx->device));
@@ -523,6 +537,10 @@ int b200_agg_read(b200_agg *a, void *values_out, uint8_t *cell_masked_out) {
     }
     B200_CUDA(cudaSetDevice(a->ctx->device));
     B200_CHECK(b200_ctx_sync(a->ctx, -1));
+    if (a->op == B200_AGG_LIST) {
+        set_error("b200_agg_read: list aggregators are read with b200_agg_list_finish / b200_agg_list_read");
+        return B200_ERR_UNSUPPORTED;
+    }
     const int rdt = b200_agg_result_dtype(a);
     const int rsz = dtype_size(rdt), csz = dtype_size(a->cell_dtype);
     if (!a->cells)
@@ -608,6 +626,8 @@ int b200_agg_merge(b200_agg *a, b200_agg *const *others, int nothers) {
         set_error("merge not implemented"); // src/agg_nunique.cpp:43-46
         return B200_ERR_UNSUPPORTED;
     }
+    if (a->op == B200_AGG_LIST)
+        return B200_OK; // AggListPrimitive::merge is empty (src/agg_list.cpp:46)
     B200_CUDA(cudaSetDevice(a->ctx->device));
     B200_CHECK(b200_ctx_sync(a->ctx, -1));
     cudaStream_t st = a->ctx->slots[0]->stream;
@@ -893,6 +913,10 @@ int b200_bin(b200_ctx *ctx, int slot, const b200_binner *binners, int nbinners, 
                 B200_CHECK(launch_first(ctx, st, fp, v));
                 B200_CUDA(cudaEventRecord(a->chain, st));
             }
+            continue;
+        }
+        if (a->op == B200_AGG_LIST) {
+            B200_CHECK(bin_list(ctx, sl, a, db, nbinners, stg.dev(aggs[k].data), static_cast<const uint8_t *>(stg.dev(aggs[k].mask)), nrows, vec));
             continue;
         }
         if (a->op == B200_AGG_NUNIQUE) {

@@ -120,6 +120,11 @@ struct b200_agg {
     unsigned long long *ntotal = nullptr;  // device counter: pairs in the table
     uint64_t npairs = 0;                   // host copy, refreshed after every launch
     std::mutex nmu;                        // growth needs the table to itself
+    // LIST (list.cu): one record per row {cell * 4 + category, value bits}, appended per call, sorted when the result is asked for
+    unsigned long long *list_keys = nullptr, *list_vals = nullptr;
+    unsigned *list_counts = nullptr;       // after finish: exclusive offsets per cell (+ the total)
+    uint64_t list_n = 0, list_cap = 0, list_total = 0;
+    bool list_sorted = false;
 };
 
 namespace b200 {

@@ -242,6 +242,11 @@ class Frame:
     def last(self, expression, order_expression=None, binby=None, limits=None, shape=128, selection=None, edges=False):
         return self._agg(_agg.last(expression, order_expression), binby, limits, shape, selection, edges)
 
+    def list(self, expression, binby=None, limits=None, shape=128, selection=None, edges=False, dropna=False, dropnan=False, dropmissing=False):
+        """df.groupby / binby with vaex.agg.list: per bin the values of `expression` (a pyarrow large_list array over the flat grid,
+        first binner fastest; vaex/agg.py:654-674)"""
+        return self._agg(_agg.list(expression, dropna=dropna, dropnan=dropnan, dropmissing=dropmissing), binby, limits, shape, selection, True)
+
     def nunique(self, expression, binby=None, limits=None, shape=128, selection=None, edges=False, dropna=False, dropnan=False, dropmissing=False):
         """df.nunique (vaex/dataframe.py nunique -> agg.nunique -> AggNUnique_<dtype>, src/agg_nunique.cpp)."""
         return self._agg(_agg.nunique(expression, dropna=dropna, dropnan=dropnan, dropmissing=dropmissing), binby, limits, shape, selection, edges)

@@ -162,11 +162,44 @@ class _BinnerHash(Binner):
         return [col] + ([m] if m is not None else [])
 
 
+class BinnerCombined:
+    """``vaex.superagg.BinnerCombined(threads, binners)`` (src/binner_combined.cpp:5-36): a binner made of several binners whose
+    indices are composed with strides 1, shape_0, shape_0 * shape_1, ... (``to_bins`` :25-29).  The reference binds it WITHOUT the
+    Binner base class (:40-44), so its own ``Grid`` cannot take one; here a Grid simply flattens it into its members, which is what
+    the composed strides amount to.  ``len()`` reports the LAST member's shape, like the reference's ``shape()`` (:31)."""
+
+    def __init__(self, threads, binners):
+        self.threads = int(threads)
+        self.binners = list(binners)
+        self.expression = ""
+        self.shapes = [len(b) for b in self.binners]
+        self.strides = []
+        s = 1
+        for n in self.shapes:
+            self.strides.append(s)
+            s *= n
+
+    def copy(self):
+        return BinnerCombined(self.threads, self.binners)
+
+    def __len__(self):
+        return self.shapes[-1]
+
+    def data_length(self, thread):
+        return self.binners[0].data_length(thread)
+
+    def __reduce__(self):
+        return (BinnerCombined, (self.threads, self.binners))
+
+
 class Grid:
     """``vaex.superagg.Grid`` (src/agg.hpp:53-143): shapes/strides with the first binner fastest + the bin() driver."""
 
     def __init__(self, binners):
-        self.binners = list(binners)
+        flat = []
+        for b in binners:  # a BinnerCombined contributes its member binners, strides composed as its to_bins does
+            flat.extend(b.binners if isinstance(b, BinnerCombined) else [b])
+        self.binners = flat
         if len(self.binners) > 8:
             raise RuntimeError("at most 8 binners are supported")
         self.shapes = [len(b) for b in self.binners]
@@ -234,7 +267,7 @@ class Aggregator:
             moment = int(extra[0])
         if op == _lib.AGG_FIRST and extra and extra[0]:
             op = _lib.AGG_LAST
-        if op == _lib.AGG_NUNIQUE:  # (dropmissing, dropnan) (src/agg_nunique.cpp:14)
+        if op in (_lib.AGG_NUNIQUE, _lib.AGG_LIST):  # (dropmissing, dropnan) (src/agg_nunique.cpp:14) / (dropnan, dropnull) (src/agg_list.cpp:16)
             moment = int(bool(extra[0])) | (int(bool(extra[1])) << 1)
         self._h = C.c_void_p()
         _lib.check(_lib.lib().b200_agg_create(self._ctx._h, op, self._code, _lib.DTYPE_CODE[self._dtype2], int(self._non_native), moment, len(grid),
@@ -409,6 +442,39 @@ class _AggNUnique(Aggregator):
         return keep
 
 
+class _AggList(Aggregator):
+    """``AggList_<dtype>(grid, grids, threads, dropnan, dropnull)`` (src/agg_list.cpp:5-127, bound at :246-259): per cell the list of
+    the rows' values.  ``get_result()`` returns what the reference hands to ``vaex.arrow.convert.list_from_arrays``: a pyarrow list
+    array with one list per cell (cells in the grid's flat order, first binner fastest)."""
+    _op = _lib.AGG_LIST
+
+    def __init__(self, grid, grids, threads, dropnan=False, dropnull=False):
+        if int(grids) != 1:
+            raise RuntimeError("list aggregation only accepts 1 grid")  # src/agg_list.cpp:18-20
+        super().__init__(grid, grids, threads, dropnan, dropnull)
+
+    def result_arrays(self):
+        """(int64 offsets[cells + 1], flat values)"""
+        total = C.c_int64(0)
+        _lib.check(_lib.lib().b200_agg_list_finish(self._h, C.byref(total)))
+        offsets = np.zeros(len(self.grid) + 1, np.int64)
+        values = np.zeros(max(total.value, 1), np.dtype(self._dtype))
+        _lib.check(_lib.lib().b200_agg_list_read(self._h, offsets.ctypes.data, values.ctypes.data))
+        return offsets, values[:total.value]
+
+    def get_result(self):
+        import pyarrow as pa
+        offsets, values = self.result_arrays()
+        return pa.LargeListArray.from_arrays(pa.array(offsets), pa.array(values))
+
+    def merge(self, others):
+        pass  # src/agg_list.cpp:46
+
+    def __sizeof__(self):
+        return 0  # "cannot predict memory usage" (vaex/agg.py:306-309)
+
+
+# ---- string aggregators (src/agg_count.cpp:70-195 AggCount_string, src/agg_nunique_string.cpp AggNUnique_string) ----------------
 def _make(name, base, **attrs):
     cls = type(name, (base,), attrs)
     cls.__module__ = __name__
@@ -430,11 +496,12 @@ for _name in _DT:
         for _prefix, _op in _AGG_OPS.items():
             _make(_prefix + "_" + _sfx, Aggregator, _op=_op, **_common)
         _make("AggNUnique_" + _sfx, _AggNUnique, **_common)
+        # the reference binds AggList_<dtype>_int64 (src/agg_list.cpp:225-238: the second type is the reserved sort column's)
+        _make("AggList_" + _name + "_int64" + ("_non_native" if _nn else ""), _AggList, **_common)
         for _name2 in _DT:
             _make("AggFirst_" + _name + "_" + _name2 + ("_non_native" if _nn else ""), Aggregator, _op=_lib.AGG_FIRST, _dtype2=_name2, **_common)
 
 
-# ---- string aggregators (src/agg_count.cpp:70-195 AggCount_string, src/agg_nunique_string.cpp AggNUnique_string) ----------------
 class AggCount_string(Aggregator):
     """count(string column) = rows whose string is not null, per cell (src/agg_count.cpp:120-160).  The string column is reduced to
     its validity bytes on the host (one byte per row, the arrow bitmap unpacked); the device counts them with the ordinary

@@ -161,6 +161,16 @@ class _OrderedSet:
             _lib.check(_lib.lib().b200_set_map_ordinal(self._h, 0, col.ptr, col.length, out.ctypes.data, _lib.MEM_HOST, 0))
         return out
 
+    def map_many(self, values, offset, length, output):
+        """hash_map<T>::map_many (src/hash_primitives.hpp:567-590), the C++-side interface BinnerHash uses: the GLOBAL ordinals of
+        values[offset:offset+length] as int64 into `output` — NaN -> the NaN ordinal (or -1 when the set holds none), absent -> -1;
+        masked values are the caller's business."""
+        ordinals = self.map_ordinal(values[offset:offset + length])
+        if not isinstance(ordinals, np.ndarray):
+            ordinals = ordinals.cpu().numpy()
+        np.asarray(output)[:length] = ordinals.astype(np.int64)
+        return output
+
     def isin(self, values):
         col = _lib.column(values)
         out = np.empty(col.length, np.uint8)

@@ -1,8 +1,11 @@
 """Registration of the B200 task parts inside a real vaex installation (boundary B1).
 
-NOT EXERCISED in the build container: ``import vaex`` fails there (dask / frozendict / aplus / future are missing and
-there is no network), so this module is written against the interface in /root/reference and covered only by the
-interface-shape tests in tests/test_taskpart_interface.py.  INTEGRATION.md walks through it.
+``import vaex`` fails in the build container (dask / frozendict / aplus / future are missing and there is no network), so this
+module is written against the interface in /root/reference and EXERCISED through a stub ``vaex`` package that restates exactly the
+pieces it touches — the 'task-part-cpu' class registry (vaex/encoding.py:31-52), ``encoding.decode``, ``vaex.memory.local.agg`` and
+``vaex.array_types.to_numpy`` — in tests/test_gpu_vaex_plugin_stub.py: the spec dicts ``TaskAggregations.encode`` emits
+(vaex/tasks.py:498-504) are decoded into the B200 task parts through the registry and driven like ExecutorLocal does.
+INTEGRATION.md walks through it.
 
 How vaex finds task parts: ``vaex.cpu.register = vaex.encoding.make_class_registery('task-part-cpu')``
 (packages/vaex-core/vaex/cpu.py:21, vaex/encoding.py:31-52) keeps a dict ``snake_name -> class``; ExecutorLocal renames the
@@ -46,7 +49,8 @@ class VaexTaskPartAggregation(_tp.TaskPartAggregation):
 
     def process(self, thread_index, i1, i2, filter_mask, selection_masks, blocks):
         import vaex.array_types
-        blocks = [vaex.array_types.to_numpy(b, strict=False) for b in blocks]  # arrow -> numpy like vaex/cpu.py:691
+        from . import hash as _hash
+        blocks = [b if _hash.is_string_column(b) else vaex.array_types.to_numpy(b, strict=False) for b in blocks]  # arrow -> numpy like vaex/cpu.py:691
         sel = [None if s is None else vaex.array_types.to_numpy(s) for s in selection_masks]
         return super().process(thread_index, i1, i2, filter_mask, sel, blocks)
 
@@ -58,16 +62,17 @@ class VaexTaskPartHashmapUniqueCreate(_tp.TaskPartHashmapUniqueCreate):
     def decode(cls, encoding, spec, df, nthreads):
         dtype = _np_dtype(encoding, spec["dtype"])
         dtype_item = _np_dtype(encoding, spec["dtype_item"])
-        if dtype.kind in "OSU" or dtype_item.kind in "OSU":
-            # strings / objects are not on the B200 path: hand the task back to the reference implementation
-            import vaex.cpu
-            return _ORIGINAL["hash_map_unique_create"].decode(encoding, spec, df=df, nthreads=nthreads)
+        if dtype_item.kind in "SU" or getattr(encoding.decode("dtype", spec["dtype_item"]), "is_string", False):
+            dtype = dtype_item = np.dtype("O")  # string keys: ordered_set_string on the device (csrc/hashset.cu)
+        elif dtype.kind == "O" or dtype_item.kind == "O":
+            raise NotImplementedError("groupby on python-object columns is not on the B200 path (there is no CPU fallback)")
         return cls(df, spec["expression"], dtype, dtype_item, flatten=spec["flatten"], limit=spec["limit"], limit_raise=spec["limit_raise"],
                    selection=spec["selection"], return_inverse=spec["return_inverse"], nthreads=nthreads)
 
     def process(self, thread_index, i1, i2, filter_mask, selection_masks, blocks):
         import vaex.array_types
-        blocks = [vaex.array_types.to_numpy(b, strict=False) for b in blocks]
+        from . import hash as _hash
+        blocks = [b if _hash.is_string_column(b) else vaex.array_types.to_numpy(b, strict=False) for b in blocks]  # strings stay arrow
         return super().process(thread_index, i1, i2, filter_mask, selection_masks, blocks)
 
 
