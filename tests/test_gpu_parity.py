@@ -309,3 +309,37 @@ def test_minmax_large_unaligned_masked(oracle):
             assert np.array_equal(Frame({"v": to_device(v)[off:]}).minmax("v", raw=True), want, equal_nan=True), (dt, off, "device")
         m = rng.random(n) < 0.5
         assert np.array_equal(Frame({"v": np.ma.array(v, mask=m)}).minmax("v", raw=True), oracle.minmax(np.ma.array(v, mask=m), raw=True), equal_nan=True)
+
+
+def test_bin_index_sweep_all_fp32(oracle):
+    """EVERY one of the 2^32 float32 bit patterns (both zeros, denormals, +-inf, every NaN payload) through the ONE device
+    ``bin_index`` (csrc/device_utils.cuh) and through the clamped magic-floor variant the ring partition uses for float32 keys
+    (csrc/ringcount.cu), against the oracle's restatement of BinnerScalar::to_bins (src/binners.cpp:13-57).  x walks the patterns
+    in order, y walks them through an odd-multiplier bijection, so both dimensions (different vmin / vmax / bins) see all of
+    them; the 2-D grid goes down the ring path (2^28 rows a call), its x marginal down the small-grid kernel of csrc/fast.cu."""
+    from concurrent.futures import ThreadPoolExecutor
+    step = 1 << 28
+
+    def chunk(k):
+        i = np.arange(k * step, (k + 1) * step, dtype=np.uint64)
+        x = i.astype(np.uint32).view(np.float32)
+        y = ((i * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32)
+        return x, y
+
+    def want(k):
+        x, y = chunk(k)
+        return oracle.binby([oracle.scalar(x, -3.25, 7.5, 1500), oracle.scalar(y, -1e-3, 2.5e-3, 700)], [oracle.agg("count")], step)[0]
+
+    total = np.int64(0)
+    with ThreadPoolExecutor(8) as pool:  # the oracle is C behind ctypes: the GIL is released
+        futures = [pool.submit(want, k) for k in range(16)]
+        for k in range(16):
+            x, y = chunk(k)
+            got = b200_binby([oracle.scalar(x, -3.25, 7.5, 1500), oracle.scalar(y, -1e-3, 2.5e-3, 700)], [oracle.agg("count")], step, device=True)[0]
+            got_x = b200_binby([oracle.scalar(x, -3.25, 7.5, 1500)], [oracle.agg("count")], step, device=True)[0]
+            w = futures[k].result()
+            assert np.array_equal(w, got), f"patterns {k * step:#x}..{(k + 1) * step:#x}"
+            axis = 1 if w.shape[0] == got_x.shape[0] else 0
+            assert np.array_equal(w.sum(axis=axis), got_x)
+            total += got.sum()
+    assert int(total) == 1 << 32
