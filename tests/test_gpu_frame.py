@@ -316,3 +316,57 @@ def test_nunique_large_matches_numpy(device):
         n_nan, n_null = int(np.isnan(vals).sum()), int((inc & ~valid).sum())
         assert got[c] == distinct + (n_nan > 0) + (n_null > 0)
         assert got_drop[c] == distinct + (n_nan > 0) + (n_null > 0) - n_nan - n_null  # row counts, like the reference
+
+
+@pytest.mark.parametrize("device", [False, True])
+@pytest.mark.parametrize("sort", [False, True])
+def test_groupby_combine_recurses_past_64_bits(device, sort, oracle):
+    """vaex/groupby.py:541-548, 572-582: four keys with ~2^16 distinct values each — the cartesian product (~1.8e19) overflows
+    2^63-1, so the first three are combined, their distinct codes become one grouper and that is combined with the fourth.  Groups,
+    counts and sums against numpy; the unsorted order against the same two-stage recursion restated with the oracle's sets."""
+    import torch
+    from vaex_b200.execution import Executor
+    from vaex_b200.frame import Frame
+    rng = np.random.default_rng(29)
+    n = 700_000
+    keys = [rng.integers(0, 1 << 16, n).astype(dt) for dt in ("i8", "i4", "u2", "i8")]
+    keys[3] = keys[3] * 3 - 70_000
+    dup = rng.integers(0, n // 2, n // 2)  # half of the rows repeat an earlier combination, so groups hold > 1 row
+    for k in keys:
+        k[n // 2:] = k[dup]
+    v = rng.normal(0, 1, n)
+    cols = dict(a=keys[0], b=keys[1], c=keys[2], d=keys[3], v=v)
+    if device:
+        cols = {k: torch.from_numpy(a.astype("i4") if a.dtype == np.uint16 else a).cuda() for k, a in cols.items()}
+        keys[2] = keys[2].astype("i4")
+    df = Frame(cols, executor=Executor(nthreads=3, chunk_size=100_003))
+    gb = df.groupby(["a", "b", "c", "d"], sort=sort, combine=True)
+    sizes = [len(hm) for hm in gb.hash_maps]
+    assert sizes[0] * sizes[1] * sizes[2] * sizes[3] >= 2 ** 63 - 1 and len(gb._stages) == 2
+    out = gb.agg({"v": ["sum", "count"]})
+    rec = np.rec.fromarrays([k.astype("i8") for k in keys])
+    uniq, inv = np.unique(rec, return_inverse=True)
+    got = np.rec.fromarrays([np.asarray(out[k]).astype("i8") for k in "abcd"])
+    assert len(got) == len(uniq)
+    order = np.argsort(got)
+    assert np.array_equal(got[order], uniq)
+    np.testing.assert_array_equal(out["count"][order], np.bincount(inv))
+    np.testing.assert_allclose(out["v_sum"][order], np.bincount(inv, weights=v), rtol=1e-9, atol=1e-9)
+    if sort:
+        assert np.array_equal(order, np.arange(len(order)))
+    else:
+        sets = [oracle.OrderedSet(k.dtype.name, 7) for k in keys]
+        for s_, k in zip(sets, keys):
+            s_.update(k, None, -1, False)
+        m1 = [len(sets[1]) * len(sets[2]), len(sets[2]), 1]
+        c1 = sum(s_.map_ordinal(k).astype("i8") * m for s_, k, m in zip(sets[:3], keys[:3], m1))
+        s1 = oracle.OrderedSet("int64", 7)
+        s1.update(c1, None, -1, False)
+        c2 = s1.map_ordinal(c1).astype("i8") * len(sets[3]) + sets[3].map_ordinal(keys[3]).astype("i8")
+        s2 = oracle.OrderedSet("int64", 7)
+        s2.update(c2, None, -1, False)
+        final = s2.key_array()
+        inner = s1.key_array()[final // len(sets[3])]
+        o = [inner // m1[0], inner % m1[0] // m1[1], inner % m1[1], final % len(sets[3])]
+        for name, s_, oo in zip("abcd", sets, o):
+            assert np.array_equal(np.asarray(out[name]), s_.key_array()[oo])

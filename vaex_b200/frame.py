@@ -341,26 +341,51 @@ class GroupBy:
     _COMBINED = "__combined_codes"
 
     def _combine(self):
-        # cumulative_counts of vaex/groupby.py:548-556: decreasing products, the last multiplier is 1
-        counts = [len(hm) for hm in self.hash_maps]
-        total = 1
-        for c in counts:
-            total *= c
-        if total >= 2 ** 63 - 1:
-            raise NotImplementedError("the cartesian product of the key counts overflows 64 bits (the reference combines recursively here)")
-        multipliers = [1] * len(counts)
-        for i in range(len(counts) - 2, -1, -1):
-            multipliers[i] = multipliers[i + 1] * counts[i + 1]
+        """vaex/groupby.py:526-584.  The keys' ordinals are fused left to right for as long as the cartesian product of the key
+        counts stays below 2^63-1 (:541-548); the distinct codes of that prefix then become ONE grouper (N = the number of codes
+        that occur) that is combined with the keys that are left — the reference's recursion (:572-582), here a loop.  A later
+        stage reads the previous stage's codes as a device-evaluated column and looks them up in that stage's set."""
         df = self.df
-        codes = _hash.CombinedCodes([df.columns[name] for name in self.by], self.hash_maps, multipliers)
-        part = taskpart.TaskPartHashmapUniqueCreate(None, self._COMBINED, np.dtype("int64"), nthreads=1)
-        task = execution.Task(part)
-        ex = execution.Executor(1, chunk_size_max=df.executor.chunk_size_max)
-        ex.execute({self._COMBINED: codes}, [task], df.length, filter=df._filter)
-        hm = task.result
-        if self.sort:
-            hm = hm.sorted()  # parents are sorted, so code order == lexicographic key order
-        self.combined = (codes, hm)
+        columns = [df.columns[name] for name in self.by]
+        maps = list(self.hash_maps)
+        self._stages = []
+        while True:
+            counts = [len(hm) for hm in maps]
+            take, total = 1, counts[0]
+            while take < len(counts) and total * counts[take] < 2 ** 63 - 1:
+                total *= counts[take]
+                take += 1
+            if take < 2:
+                raise ValueError("two key counts whose product overflows 64 bits cannot be combined")  # `assert len(combine_now) >= 2`
+            # cumulative_counts (:548-556): decreasing products, the last multiplier is 1
+            multipliers = [1] * take
+            for i in range(take - 2, -1, -1):
+                multipliers[i] = multipliers[i + 1] * counts[i + 1]
+            codes = _hash.CombinedCodes(columns[:take], maps[:take], multipliers)
+            part = taskpart.TaskPartHashmapUniqueCreate(None, self._COMBINED, np.dtype("int64"), nthreads=1)
+            task = execution.Task(part)
+            ex = execution.Executor(1, chunk_size_max=df.executor.chunk_size_max)
+            ex.execute({self._COMBINED: codes}, [task], df.length, filter=df._filter)
+            hm = task.result
+            if self.sort:
+                hm = hm.sorted()  # parents are sorted, so code order == lexicographic key order (at every stage)
+            self._stages.append((codes, hm))
+            if take == len(counts):
+                break
+            columns = [codes] + columns[take:]
+            maps = [hm] + maps[take:]
+        self.combined = self._stages[-1]
+
+    def _decode(self, group_codes, level=None):
+        """group code -> ordinal of every ORIGINAL key: the div/mod chain of GrouperCombined (vaex/groupby.py:352-358), unwound
+        through the stages (a stage's first 'key' is the previous stage's code set)."""
+        level = len(self._stages) - 1 if level is None else level
+        codes, _ = self._stages[level]
+        ordinals = codes.decode(group_codes)
+        if level == 0:
+            return ordinals
+        previous = np.asarray(self._stages[level - 1][1].keys())[ordinals[0]]
+        return self._decode(previous, level - 1) + ordinals[1:]
 
     def keys(self):
         return [hm.keys() for hm in self.hash_maps]
@@ -394,7 +419,7 @@ class GroupBy:
             keep = counts > 0
             group_codes = np.asarray(chm.keys())[keep]
             out = {}
-            for name, hm, ordinals in zip(self.by, self.hash_maps, codes.decode(group_codes)):
+            for name, hm, ordinals in zip(self.by, self.hash_maps, self._decode(group_codes)):
                 out[name] = hm.keys()[ordinals]
             for label, g in zip(labels[:-1], grids[:-1]):
                 out[label] = g[:-2][keep]

@@ -233,7 +233,8 @@ class CombinedCodes:
         nk = len(self.columns)
         keep, kptr, mptr, spaces = [], (C.c_void_p * nk)(), (C.c_void_p * nk)(), set()
         for k, col in enumerate(self.columns):
-            part = col[i1:i2]
+            # a previous stage's codes (vaex/groupby.py:572-582) are produced on this worker's slot, like every device-virtual column
+            part = col.chunk(thread_index, i1, i2) if getattr(col, "device_virtual", False) else col[i1:i2]
             mask = None
             if isinstance(part, np.ndarray) and np.ma.isMaskedArray(part):
                 mask = np.ma.getmaskarray(part)
