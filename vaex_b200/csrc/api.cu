@@ -262,11 +262,18 @@ int b200_ctx_create(int device, int nslots, b200_ctx **out) {
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     for (int i = 0; i < nslots; i++) {
         Slot *s = new Slot;
-        B200_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-        B200_CUDA(cudaEventCreateWithFlags(&s->h2d_done, cudaEventDisableTiming));
-        B200_CUDA(cudaMallocHost(&s->pinned, 4096));
-        B200_CUDA(cudaMalloc(&s->dscratch, 4096));
-        ctx->slots.push_back(s);
+        ctx->slots.push_back(s); // owned by ctx from here on: a failure below is undone by b200_ctx_destroy
+        cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess)
+            e = cudaEventCreateWithFlags(&s->h2d_done, cudaEventDisableTiming);
+        if (e == cudaSuccess)
+            e = cudaMallocHost(&s->pinned, 4096);
+        if (e == cudaSuccess)
+            e = cudaMalloc(&s->dscratch, 4096);
+        if (e != cudaSuccess) {
+            b200_ctx_destroy(ctx);
+            return cuda_fail(e, "b200_ctx_create: slot resources", __FILE__, __LINE__);
+        }
     }
     *out = ctx;
     return B200_OK;
@@ -277,7 +284,8 @@ int b200_ctx_destroy(b200_ctx *ctx) {
         return B200_OK;
     cudaSetDevice(ctx->device);
     for (Slot *s : ctx->slots) {
-        cudaStreamSynchronize(s->stream);
+        if (s->stream)
+            cudaStreamSynchronize(s->stream);
         cudaFree(s->stage);
         cudaFree(s->scratch);
         cudaFree(s->dscratch);
@@ -288,8 +296,10 @@ int b200_ctx_destroy(b200_ctx *ctx) {
             if (s->bounce_done[b])
                 cudaEventDestroy(s->bounce_done[b]);
         }
-        cudaEventDestroy(s->h2d_done);
-        cudaStreamDestroy(s->stream);
+        if (s->h2d_done)
+            cudaEventDestroy(s->h2d_done);
+        if (s->stream)
+            cudaStreamDestroy(s->stream);
         delete s;
     }
     delete ctx;
@@ -617,6 +627,13 @@ int b200_agg_write(b200_agg *a, const void *values) {
     return B200_OK;
 }
 
+namespace {
+struct DeviceTemp {
+    void *p = nullptr;
+    ~DeviceTemp() { cudaFree(p); }
+};
+} // namespace
+
 int b200_agg_merge(b200_agg *a, b200_agg *const *others, int nothers) {
     if (!a || (nothers && !others)) {
         set_error("b200_agg_merge: invalid argument");
@@ -641,7 +658,8 @@ int b200_agg_merge(b200_agg *a, b200_agg *const *others, int nothers) {
             B200_CHECK(b200_ctx_sync(o->ctx, -1));
         // same-process peers on other devices are read through UVA peer access when enabled; keep it simple: stage through host
         const void *src = o->grid;
-        void *tmp = nullptr, *tstate = nullptr, *torder = nullptr, *tmask = nullptr;
+        DeviceTemp tmp_, tstate_, torder_, tmask_; // freed on every way out of this iteration
+        void *&tmp = tmp_.p, *&tstate = tstate_.p, *&torder = torder_.p, *&tmask = tmask_.p;
         b200_agg view; // shallow alias of `o` (b200_agg is not copyable: it owns a mutex)
         view.ctx = o->ctx, view.op = o->op, view.dtype = o->dtype, view.dtype2 = o->dtype2, view.byteswap = o->byteswap, view.moment = o->moment;
         view.cells = o->cells, view.cell_dtype = o->cell_dtype, view.grid = o->grid, view.state = o->state, view.order = o->order, view.cell_masked = o->cell_masked;
@@ -670,10 +688,6 @@ int b200_agg_merge(b200_agg *a, b200_agg *const *others, int nothers) {
             rc = launch_merge(st, a->op, a->cell_dtype, a->grid, src, a->cells);
         if (!rc && cudaStreamSynchronize(st) != cudaSuccess)
             rc = B200_ERR_CUDA;
-        cudaFree(tmp);
-        cudaFree(tstate);
-        cudaFree(torder);
-        cudaFree(tmask);
         B200_CHECK(rc);
     }
     return B200_OK;

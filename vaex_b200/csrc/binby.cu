@@ -257,6 +257,10 @@ int try_launch_ringcount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool ve
 int launch_binby(b200_ctx *ctx, Slot *slot, const BinParams &p, bool vec) {
     if (p.nrows <= 0)
         return B200_OK;
+    if (p.nrows >= (1ll << 38)) { // the shared-memory sub-histograms count in 32 bits per CTA: >= 148 CTAs keep a CTA's share below 2^31
+        set_error("b200_bin: %lld rows in one call (the limit is 2^38; a B200 holds < 2^38 rows of any column)", (long long)p.nrows);
+        return B200_ERR_INVALID;
+    }
     cudaStream_t stream = slot->stream;
     // B200_DISABLE_FAST=1 forces the descriptor-driven kernel (A/B measurements, parity tests of both kernels)
     static const bool disable_fast = getenv("B200_DISABLE_FAST") && atoi(getenv("B200_DISABLE_FAST")) != 0;

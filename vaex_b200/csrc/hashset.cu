@@ -678,13 +678,19 @@ int b200_set_create(b200_ctx *ctx, int dtype, int nmaps, int64_t limit, b200_set
     cudaStream_t st = ctx->slots[0]->stream;
     int rc = set_alloc_table(s, 1ull << 12, st);
     if (rc) {
-        delete s;
+        b200_set_destroy(s);
         return rc;
     }
-    B200_CUDA(cudaMalloc(&s->d_ctr, sizeof(unsigned long long) * CTR_N));
     unsigned long long init[CTR_N] = {0, 0, 0, 0, ~0ull, ~0ull, ~0ull, 0, 0, 0};
-    B200_CUDA(cudaMemcpyAsync(s->d_ctr, init, sizeof init, cudaMemcpyHostToDevice, st));
-    B200_CUDA(cudaStreamSynchronize(st));
+    cudaError_t e = cudaMalloc(&s->d_ctr, sizeof(unsigned long long) * CTR_N);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(s->d_ctr, init, sizeof init, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        b200_set_destroy(s); // the set and its table do not outlive a failed create
+        return cuda_fail(e, "b200_set_create: counters", __FILE__, __LINE__);
+    }
     *out = s;
     return B200_OK;
 }
@@ -695,9 +701,16 @@ int b200_counter_create(b200_ctx *ctx, int dtype, int nmaps, b200_set **out) {
     b200_set *s = *out;
     s->counting = true;
     cudaStream_t st = ctx->slots[0]->stream;
-    B200_CUDA(cudaMalloc(&s->counts, s->cap * sizeof(unsigned long long)));
-    B200_CUDA(cudaMemsetAsync(s->counts, 0, s->cap * sizeof(unsigned long long), st));
-    B200_CUDA(cudaStreamSynchronize(st));
+    cudaError_t e = cudaMalloc(&s->counts, s->cap * sizeof(unsigned long long));
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(s->counts, 0, s->cap * sizeof(unsigned long long), st);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        b200_set_destroy(s);
+        *out = nullptr;
+        return cuda_fail(e, "b200_counter_create: counts", __FILE__, __LINE__);
+    }
     return B200_OK;
 }
 
