@@ -136,6 +136,10 @@ int b200_ctx_stream(b200_ctx *ctx, int slot, void **stream_out);
  * out[2] chunks reserved, out[3] entries per chunk, out[4] bytes memset before the batch, out[5] (warp, part) lists.
  * All zero when the slot has not run that path.  No reference counterpart (instrumentation). */
 int b200_ctx_path_stats(b200_ctx *ctx, int slot, uint64_t out[6]);
+/* Wall-clock accounting of the host-chunk path (b200_bin with B200_MEM_HOST), summed over the slots: out[0..3] nanoseconds spent
+ * waiting for a free piece of the page-locked bounce ring, in memcpy into the ring, enqueueing the pieces' copies, and in b200_bin
+ * as a whole; out[4] pieces copied, out[5] calls.  reset != 0 zeroes the counters.  No reference counterpart (instrumentation). */
+int b200_ctx_host_stats(b200_ctx *ctx, uint64_t out[6], int reset);
 
 /* ---- aggregators --------------------------------------------------------------------------- */
 int b200_agg_create(b200_ctx *ctx, int op, int dtype, int dtype2, int byteswap, uint32_t moment, uint64_t cells, b200_agg **out);

@@ -104,6 +104,7 @@ def lib():
             "b200_ctx_device": (i32, [vp]),
             "b200_ctx_stream": (i32, [vp, i32, P(vp)]),
             "b200_ctx_path_stats": (i32, [vp, i32, P(u64)]),
+            "b200_ctx_host_stats": (i32, [vp, P(u64), i32]),
             "b200_agg_create": (i32, [vp, i32, i32, i32, i32, u32, u64, P(vp)]),
             "b200_agg_destroy": (i32, [vp]),
             "b200_agg_reset": (i32, [vp]),
@@ -199,6 +200,12 @@ class Context:
         out = (C.c_uint64 * 6)()
         check(lib().b200_ctx_path_stats(self._h, int(slot), out))
         return dict(rows=out[0], entries=out[1], chunks=out[2], chunk_entries=out[3], memset_bytes=out[4], lists=out[5])
+
+    def host_stats(self, reset=False):
+        """Where the host-chunk path spent its wall time (include/b200agg.h b200_ctx_host_stats), milliseconds summed over slots."""
+        out = (C.c_uint64 * 6)()
+        check(lib().b200_ctx_host_stats(self._h, out, int(bool(reset))))
+        return dict(wait_ms=out[0] / 1e6, memcpy_ms=out[1] / 1e6, enqueue_ms=out[2] / 1e6, bin_ms=out[3] / 1e6, pieces=out[4], calls=out[5])
 
     def stream(self, slot=0):
         s = C.c_void_p()

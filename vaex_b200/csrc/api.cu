@@ -2,7 +2,10 @@
 #include <math.h>
 #include <stdarg.h>
 
+#include <immintrin.h>
+
 #include <algorithm>
+#include <chrono>
 
 #include "binby.cuh"
 #include "device_utils.cuh"
@@ -26,6 +29,35 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 }
 
 // ---- staging of host chunks -----------------------------------------------------------------------
+// Host column -> page-locked ring piece.  The piece is read next by the copy engine, not by a core: non-temporal stores keep it out
+// of the caches and save the read-for-ownership of every destination line, which is what bounds glibc's memcpy when 16 feeder
+// threads copy at once (measured: tools/probe_e2e_threads.py, profiles/r02_e2e_probe.txt).  `dst` is 64-byte aligned (the ring is
+// page-locked memory, pieces start at multiples of the piece size); the sfence makes the stores visible before the DMA is enqueued.
+__attribute__((target("avx2"))) static void copy_stream_avx2(char *dst, const char *src, size_t n) {
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 64));
+        const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 96), d);
+    }
+    _mm_sfence();
+    if (i < n)
+        memcpy(dst + i, src + i, n - i);
+}
+
+static void copy_to_ring(void *dst, const void *src, size_t n) {
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !(getenv("B200_BOUNCE_MEMCPY") && atoi(getenv("B200_BOUNCE_MEMCPY")));
+    if (avx2 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0)
+        copy_stream_avx2(static_cast<char *>(dst), static_cast<const char *>(src), n);
+    else
+        memcpy(dst, src, n);
+}
+
 int slot_reserve(b200_ctx *ctx, Slot *s, size_t bytes) {
     if (bytes <= s->stage_cap)
         return B200_OK;
@@ -40,6 +72,47 @@ int slot_reserve(b200_ctx *ctx, Slot *s, size_t bytes) {
     s->stage_cap = cap;
     (void)ctx;
     return B200_OK;
+}
+
+cudaError_t ctx_alloc(b200_ctx *ctx, void **out, size_t bytes) {
+    bytes = align_up(bytes ? bytes : 1, 256);
+    {
+        std::lock_guard<std::mutex> g(ctx->cache_mu);
+        auto it = ctx->cache.find(bytes);
+        if (it != ctx->cache.end()) {
+            *out = it->second;
+            ctx->cache.erase(it);
+            ctx->cache_bytes -= bytes;
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) { // give the cache back before reporting out-of-memory
+        cudaGetLastError();
+        std::lock_guard<std::mutex> g(ctx->cache_mu);
+        for (auto &kv : ctx->cache)
+            cudaFree(kv.second);
+        ctx->cache.clear();
+        ctx->cache_bytes = 0;
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
+}
+
+void ctx_release(b200_ctx *ctx, void *p, size_t bytes) {
+    if (!p)
+        return;
+    bytes = align_up(bytes ? bytes : 1, 256);
+    constexpr size_t kCacheLimit = 4ull << 30; // per context; a block larger than a quarter of it is never kept
+    {
+        std::lock_guard<std::mutex> g(ctx->cache_mu);
+        if (bytes <= kCacheLimit / 4 && ctx->cache_bytes + bytes <= kCacheLimit) {
+            ctx->cache.emplace(bytes, p);
+            ctx->cache_bytes += bytes;
+            return;
+        }
+    }
+    cudaFree(p);
 }
 
 bool is_device_pointer(const void *p) {
@@ -75,34 +148,41 @@ int Stager::commit() {
     // MIXED keeps per-column copies (some columns are device pointers and were not planned); HOST chunks whose buffers die with
     // the call go through the slot's page-locked bounce ring
     const bool bounce = !async_host && memspace == B200_MEM_HOST;
-    char *pin = nullptr;
     if (bounce) {
-        const unsigned b = slot->bounce_next++ & 1u;
-        if (!slot->bounce_done[b])
-            B200_CUDA(cudaEventCreateWithFlags(&slot->bounce_done[b], cudaEventDisableTiming));
-        B200_CUDA(cudaEventSynchronize(slot->bounce_done[b])); // the copy that last read this buffer has finished
-        if (slot->bounce_cap[b] < need) {
-            if (slot->bounce[b])
-                B200_CUDA(cudaFreeHost(slot->bounce[b]));
-            slot->bounce[b] = nullptr;
-            slot->bounce_cap[b] = 0;
-            const size_t cap = align_up(need + need / 4, 1 << 20);
-            B200_CUDA(cudaHostAlloc(&slot->bounce[b], cap, cudaHostAllocPortable));
-            slot->bounce_cap[b] = cap;
-        }
-        pin = static_cast<char *>(slot->bounce[b]);
-        // pieces of 4 MB: the asynchronous copy of one piece runs while this thread memcpy's the next one
-        constexpr size_t kPiece = 4u << 20;
+        // B200_BOUNCE_PIECE_KB / B200_BOUNCE_COUNT: ring geometry (defaults 4 MB x 4)
+        static const size_t piece = getenv("B200_BOUNCE_PIECE_KB") ? std::max<size_t>(64, atol(getenv("B200_BOUNCE_PIECE_KB"))) << 10 : 4u << 20;
+        static const unsigned count = getenv("B200_BOUNCE_COUNT") ? std::min<unsigned>(Slot::kBounceMax, std::max(2, atoi(getenv("B200_BOUNCE_COUNT")))) : 4u;
+        using clk = std::chrono::steady_clock;
+        auto ns = [](clk::time_point a, clk::time_point b) { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
         for (auto &e : entries) {
             e.dev = static_cast<char *>(slot->stage) + off;
-            for (size_t q = 0; q < e.bytes; q += kPiece) {
-                const size_t len = std::min(kPiece, e.bytes - q);
-                memcpy(pin + off + q, static_cast<const char *>(e.host) + q, len);
-                B200_CUDA(cudaMemcpyAsync(static_cast<char *>(e.dev) + q, pin + off + q, len, cudaMemcpyHostToDevice, slot->stream));
+            for (size_t q = 0; q < e.bytes; q += piece) {
+                const size_t len = std::min(piece, e.bytes - q);
+                const unsigned b = slot->bounce_next++ % count;
+                const auto t0 = clk::now();
+                if (slot->bounce_cap[b] < piece) {
+                    if (slot->bounce[b]) {
+                        B200_CUDA(cudaEventSynchronize(slot->bounce_done[b]));
+                        B200_CUDA(cudaFreeHost(slot->bounce[b]));
+                        slot->bounce[b] = nullptr, slot->bounce_cap[b] = 0;
+                    }
+                    B200_CUDA(cudaHostAlloc(&slot->bounce[b], piece, cudaHostAllocPortable));
+                    slot->bounce_cap[b] = piece;
+                    if (!slot->bounce_done[b])
+                        B200_CUDA(cudaEventCreateWithFlags(&slot->bounce_done[b], cudaEventDisableTiming));
+                } else {
+                    B200_CUDA(cudaEventSynchronize(slot->bounce_done[b])); // the copy that last read this piece has finished
+                }
+                const auto t1 = clk::now();
+                copy_to_ring(slot->bounce[b], static_cast<const char *>(e.host) + q, len);
+                const auto t2 = clk::now();
+                B200_CUDA(cudaMemcpyAsync(static_cast<char *>(e.dev) + q, slot->bounce[b], len, cudaMemcpyHostToDevice, slot->stream));
+                B200_CUDA(cudaEventRecord(slot->bounce_done[b], slot->stream));
+                const auto t3 = clk::now();
+                slot->host_ns[0] += ns(t0, t1), slot->host_ns[1] += ns(t1, t2), slot->host_ns[2] += ns(t2, t3), slot->host_pieces++;
             }
             off += align_up(e.bytes, 256);
         }
-        B200_CUDA(cudaEventRecord(slot->bounce_done[b], slot->stream));
         return B200_OK;
     }
     for (auto &e : entries) {
@@ -290,7 +370,7 @@ int b200_ctx_destroy(b200_ctx *ctx) {
         cudaFree(s->scratch);
         cudaFree(s->dscratch);
         cudaFreeHost(s->pinned);
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < Slot::kBounceMax; b++) {
             if (s->bounce[b])
                 cudaFreeHost(s->bounce[b]);
             if (s->bounce_done[b])
@@ -302,6 +382,8 @@ int b200_ctx_destroy(b200_ctx *ctx) {
             cudaStreamDestroy(s->stream);
         delete s;
     }
+    for (auto &kv : ctx->cache)
+        cudaFree(kv.second);
     delete ctx;
     return B200_OK;
 }
@@ -380,7 +462,27 @@ int b200_ctx_path_stats(b200_ctx *ctx, int slot, uint64_t out[6]) {
     return B200_OK;
 }
 
+int b200_ctx_host_stats(b200_ctx *ctx, uint64_t out[6], int reset) {
+    if (!ctx || !out) {
+        set_error("b200_ctx_host_stats: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    memset(out, 0, 6 * sizeof(uint64_t));
+    for (Slot *s : ctx->slots) {
+        std::lock_guard<std::mutex> g(s->mu);
+        for (int k = 0; k < 4; k++)
+            out[k] += s->host_ns[k];
+        out[4] += s->host_pieces, out[5] += s->host_calls;
+        if (reset)
+            s->host_ns[0] = s->host_ns[1] = s->host_ns[2] = s->host_ns[3] = s->host_pieces = s->host_calls = 0;
+    }
+    return B200_OK;
+}
+
 // ---- aggregators -----------------------------------------------------------------------------------
+static size_t agg_cells_alloc(const b200_agg *a) { return a->op == B200_AGG_LIST ? 16 : (a->cells ? a->cells : 1); }
+static size_t agg_grid_bytes(const b200_agg *a) { return agg_cells_alloc(a) * dtype_size(a->cell_dtype) * (a->op == B200_AGG_NUNIQUE ? 3 : 1); }
+
 int b200_agg_create(b200_ctx *ctx, int op, int dtype, int dtype2, int byteswap, uint32_t moment, uint64_t cells, b200_agg **out) {
     if (!ctx || !out || op < B200_AGG_COUNT || op > B200_AGG_LIST || dtype < 0 || dtype >= B200_NDTYPE || dtype2 < 0 || dtype2 >= B200_NDTYPE) {
         set_error("b200_agg_create: invalid argument");
@@ -406,15 +508,15 @@ int b200_agg_create(b200_ctx *ctx, int op, int dtype, int dtype2, int byteswap, 
     default: a->cell_dtype = dtype; break;
     }
     const size_t n = op == B200_AGG_LIST ? 16 : (cells ? cells : 1);
-    cudaError_t e = cudaMalloc(&a->grid, n * dtype_size(a->cell_dtype) * (op == B200_AGG_NUNIQUE ? 3 : 1));
+    cudaError_t e = ctx_alloc(ctx, &a->grid, agg_grid_bytes(a));
     if (e == cudaSuccess && op == B200_AGG_NUNIQUE)
         e = cudaMalloc((void **)&a->ntotal, 8);
     if (e == cudaSuccess && (op == B200_AGG_FIRST || op == B200_AGG_LAST)) {
-        e = cudaMalloc(&a->state, n * 16);
+        e = ctx_alloc(ctx, &a->state, n * 16);
         if (e == cudaSuccess)
-            e = cudaMalloc(&a->order, n * dtype_size(dtype2));
+            e = ctx_alloc(ctx, &a->order, n * dtype_size(dtype2));
         if (e == cudaSuccess)
-            e = cudaMalloc((void **)&a->cell_masked, n);
+            e = ctx_alloc(ctx, (void **)&a->cell_masked, n);
         if (e == cudaSuccess)
             e = cudaEventCreateWithFlags(&a->chain, cudaEventDisableTiming);
     }
@@ -443,10 +545,14 @@ int b200_agg_destroy(b200_agg *a) {
     if (!a)
         return B200_OK;
     cudaSetDevice(a->ctx->device);
-    cudaFree(a->grid);
-    cudaFree(a->state);
-    cudaFree(a->order);
-    cudaFree(a->cell_masked);
+    // the cell-shaped buffers go back to the context's cache: nothing in flight may still touch them
+    for (Slot *s : a->ctx->slots)
+        cudaStreamSynchronize(s->stream);
+    const size_t n = agg_cells_alloc(a);
+    ctx_release(a->ctx, a->grid, agg_grid_bytes(a));
+    ctx_release(a->ctx, a->state, n * 16);
+    ctx_release(a->ctx, a->order, n * dtype_size(a->dtype2));
+    ctx_release(a->ctx, a->cell_masked, n);
     cudaFree(a->ntable);
     cudaFree(a->ntotal);
     cudaFree(a->list_keys);
@@ -826,6 +932,14 @@ int b200_bin(b200_ctx *ctx, int slot, const b200_binner *binners, int nbinners, 
     Slot *sl = ctx->slots[slot];
     std::lock_guard<std::mutex> guard(sl->mu);
     cudaStream_t st = sl->stream;
+    struct HostTimer { // wall time of HOST calls on this slot, for b200_ctx_host_stats
+        Slot *s;
+        std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        ~HostTimer() {
+            if (s)
+                s->host_ns[3] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(), s->host_calls++;
+        }
+    } host_timer{memspace == B200_MEM_HOST ? sl : nullptr};
 
     // stage host columns (each distinct pointer once)
     Stager stg{ctx, sl, memspace};

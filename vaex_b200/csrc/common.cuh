@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -74,13 +75,19 @@ struct Slot {
     void *stage = nullptr; // device staging arena for host chunks
     size_t stage_cap = 0;
     void *pinned = nullptr; // small pinned scratch (results of reductions)
-    // host-chunk ingestion: two page-locked bounce buffers; a host column is memcpy'd into one of them by the calling thread and
-    // travels to the arena with ONE asynchronous copy, so the call returns without waiting for the device (the caller's buffer
-    // is only valid during the call, vaex/cpu.py:708-710)
-    void *bounce[2] = {nullptr, nullptr};
-    size_t bounce_cap[2] = {0, 0};
-    cudaEvent_t bounce_done[2] = {nullptr, nullptr};
+    // host-chunk ingestion: a ring of kBounce page-locked pieces of kBouncePiece bytes.  The calling thread memcpy's a host column
+    // piece by piece into the ring and every piece travels to the arena with its own asynchronous copy, so the call returns without
+    // waiting for the device (the caller's buffer is only valid during the call, vaex/cpu.py:708-710).  The ring is small on
+    // purpose (16 MB a slot whatever the chunk size): the pieces stay in the host's last-level cache between the memcpy that writes
+    // them and the DMA that reads them, and no chunk-sized page-locked allocation is ever made.
+    static constexpr int kBounceMax = 16;
+    void *bounce[kBounceMax] = {};
+    size_t bounce_cap[kBounceMax] = {};
+    cudaEvent_t bounce_done[kBounceMax] = {};
     unsigned bounce_next = 0;
+    // wall-clock nanoseconds of the host-chunk path on this slot (b200_ctx_host_stats): waiting for a ring piece, memcpy into it,
+    // enqueueing its copy, the whole of b200_bin; pieces and calls
+    uint64_t host_ns[4] = {0, 0, 0, 0}, host_pieces = 0, host_calls = 0;
     void *dscratch = nullptr;
     void *scratch = nullptr; // partition scratch (ringcount pool + list tables, tilesort buckets)
     size_t scratch_cap = 0;
@@ -99,6 +106,13 @@ struct b200_ctx {
     int sm_count = 148;
     size_t smem_optin = 0;
     std::vector<b200::Slot *> slots;
+    // Grid cache: an aggregation pass creates its aggregators and destroys them when the result has been read (vaex builds a task
+    // part per pass), and cudaMalloc / cudaFree synchronise the device and take the driver's allocation lock — measured at up to
+    // 45 ms a call while 16-32 feeder threads are enqueueing copies (profiles/r02_e2e_probe.txt).  Released grids are kept by exact
+    // size (bounded) and handed to the next pass.
+    std::mutex cache_mu;
+    std::multimap<size_t, void *> cache;
+    size_t cache_bytes = 0;
 };
 
 struct b200_agg {
@@ -150,6 +164,9 @@ struct Stager {
 };
 
 int slot_reserve(b200_ctx *ctx, Slot *s, size_t bytes);
+// grid cache of the context (api.cu): cudaMalloc on a miss; a released block must not be referenced by work in flight
+cudaError_t ctx_alloc(b200_ctx *ctx, void **out, size_t bytes);
+void ctx_release(b200_ctx *ctx, void *p, size_t bytes);
 bool is_device_pointer(const void *p);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
