@@ -457,7 +457,7 @@ int set_finalize(b200_set *s) {
         return B200_ERR_UNSUPPORTED;
     }
     // one allocation: ckey | tag A | val A | tag B | val B | radix histograms | shard starts | special ordinals
-    const unsigned nblk = (unsigned)((E + kRadixThreads - 1) / kRadixThreads);
+    const unsigned nblk = radix_blocks(E);
     const size_t en = (size_t)(E ? E : 1);
     const size_t off_hist = 5 * en * 8, off_first = off_hist + align_up((size_t)256 * (nblk ? nblk : 1) * 4, 256), off_spec = off_first + align_up((size_t)s->nmaps * 8, 256);
     char *work = nullptr;
@@ -500,9 +500,9 @@ int set_finalize(b200_set *s) {
     }
     unsigned long long *tin = tagA, *vin = valA, *tout = tagB, *vout = valB;
     auto pass = [&](int shift, int from_val) -> int {
-        k_radix_hist<<<nblk, kRadixThreads, 0, st>>>(tin, vin, E, shift, from_val, hist, nblk);
+        k_radix_hist<<<nblk, kRadixThreads, 0, st>>>(tin, vin, E, shift, from_val, hist, nblk, radix_tiles(E));
         k_scan_u32<<<1, 1024, 0, st>>>(hist, 256ull * nblk);
-        k_radix_scatter<<<nblk, kRadixThreads, 0, st>>>(tin, vin, tout, vout, E, shift, from_val, hist, nblk);
+        k_radix_scatter<<<nblk, kRadixThreads, 0, st>>>(tin, vin, tout, vout, E, shift, from_val, hist, nblk, radix_tiles(E));
         B200_CUDA(cudaGetLastError());
         std::swap(tin, tout);
         std::swap(vin, vout);

@@ -168,7 +168,7 @@ int b200_agg_list_finish(b200_agg *a, int64_t *total_out) {
             set_error("AggList: more than 2^32 rows are not supported");
             return B200_ERR_UNSUPPORTED;
         }
-        const unsigned nblk = (unsigned)((n + kRadixThreads - 1) / kRadixThreads);
+        const unsigned nblk = radix_blocks(n), tiles = radix_tiles(n);
         unsigned long long *kb = nullptr, *vb = nullptr;
         unsigned *hist = nullptr;
         B200_CUDA(cudaMalloc(&kb, n * 8));
@@ -178,9 +178,9 @@ int b200_agg_list_finish(b200_agg *a, int64_t *total_out) {
         // keys are cell * 4 + category (skipped rows: cells * 4): only the bytes that can differ are sorted on
         const unsigned long long maxkey = a->cells * 4 + 3;
         for (int shift = 0; shift < 64 && (maxkey >> shift); shift += 8) {
-            k_radix_hist<<<nblk, kRadixThreads, 0, st>>>(kin, vin, n, shift, 0, hist, nblk);
+            k_radix_hist<<<nblk, kRadixThreads, 0, st>>>(kin, vin, n, shift, 0, hist, nblk, tiles);
             k_scan_u32<<<1, 1024, 0, st>>>(hist, 256ull * nblk);
-            k_radix_scatter<<<nblk, kRadixThreads, 0, st>>>(kin, vin, kout, vout, n, shift, 0, hist, nblk);
+            k_radix_scatter<<<nblk, kRadixThreads, 0, st>>>(kin, vin, kout, vout, n, shift, 0, hist, nblk, tiles);
             B200_CUDA(cudaGetLastError());
             std::swap(kin, kout);
             std::swap(vin, vout);
