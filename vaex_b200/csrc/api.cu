@@ -74,8 +74,20 @@ int slot_reserve(b200_ctx *ctx, Slot *s, size_t bytes) {
     return B200_OK;
 }
 
-cudaError_t ctx_alloc(b200_ctx *ctx, void **out, size_t bytes) {
+// size classes of the cache: exact (256-byte granules) up to 1 MB, above that 8 steps per power of two (<= 12.5 % slack), so
+// buffers whose size depends on a key count (hash tables, sort scratch) find a block again when the count moves a little
+static size_t cache_class(size_t bytes) {
     bytes = align_up(bytes ? bytes : 1, 256);
+    if (bytes <= (1u << 20))
+        return bytes;
+    size_t step = 1;
+    while ((step << 4) <= bytes)
+        step <<= 1; // step = 2^(floor(log2 bytes) - 3)
+    return align_up(bytes, step);
+}
+
+cudaError_t ctx_alloc(b200_ctx *ctx, void **out, size_t bytes) {
+    bytes = cache_class(bytes);
     {
         std::lock_guard<std::mutex> g(ctx->cache_mu);
         auto it = ctx->cache.find(bytes);
@@ -102,7 +114,7 @@ cudaError_t ctx_alloc(b200_ctx *ctx, void **out, size_t bytes) {
 void ctx_release(b200_ctx *ctx, void *p, size_t bytes) {
     if (!p)
         return;
-    bytes = align_up(bytes ? bytes : 1, 256);
+    bytes = cache_class(bytes);
     constexpr size_t kCacheLimit = 4ull << 30; // per context; a block larger than a quarter of it is never kept
     {
         std::lock_guard<std::mutex> g(ctx->cache_mu);

@@ -45,6 +45,7 @@ struct b200_set {
     std::vector<uint64_t> h_keys;   // canonical patterns in ordinal order (special slots hold 0); filled lazily from d_keys_ord
     bool h_keys_valid = false;
     unsigned long long *d_keys_ord = nullptr; // n_entries canonical patterns in ordinal order (device)
+    size_t keys_ord_bytes = 0, log_bytes = 0;  // sizes handed to ctx_alloc (the blocks go back to the context's cache)
     uint64_t n_entries = 0;                   // keys + NaN + null slots
     int64_t max_call_rows = 0;                // largest update so far: bounds the row part of every tag
     // string keys (ordered_set_string): the table's key is the reference's 64-bit string hash; the bytes of every distinct key live
@@ -383,42 +384,43 @@ inline int nblocks(unsigned long long n, int threads = 256) {
     return (int)(b < 148ull * 8 ? (b ? b : 1) : 148ull * 8);
 }
 
+// Tables, sort scratch and probe tables come from the context's block cache (ctx_alloc, api.cu): a groupby builds and drops a set per
+// key column and pass, and cudaMalloc / cudaFree synchronise the device and contend with the feeder threads' copies.
 int set_alloc_table(b200_set *s, uint64_t cap, cudaStream_t st) {
-    B200_CUDA(cudaMalloc(&s->table, cap * sizeof(SetSlot)));
+    B200_CUDA(ctx_alloc(s->ctx, reinterpret_cast<void **>(&s->table), cap * sizeof(SetSlot)));
     s->cap = cap;
     if (s->counting) {
-        B200_CUDA(cudaMalloc(&s->counts, cap * sizeof(unsigned long long)));
+        B200_CUDA(ctx_alloc(s->ctx, reinterpret_cast<void **>(&s->counts), cap * sizeof(unsigned long long)));
         B200_CUDA(cudaMemsetAsync(s->counts, 0, cap * sizeof(unsigned long long), st));
     }
     if (s->strings)
-        B200_CUDA(cudaMalloc(&s->slot_log, cap * sizeof(unsigned)));
+        B200_CUDA(ctx_alloc(s->ctx, reinterpret_cast<void **>(&s->slot_log), cap * sizeof(unsigned)));
     k_set_init<<<nblocks(cap), 256, 0, st>>>(s->table, cap);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
 
-int set_grow(b200_set *s, cudaStream_t st) {
+int set_grow(b200_set *s, cudaStream_t st, uint64_t new_cap = 0) {
     SetSlot *old = s->table;
     unsigned long long *old_counts = s->counts;
     unsigned *old_slot_log = s->slot_log;
     StrLog *old_log = s->log;
+    const size_t old_log_bytes = s->log_bytes;
     uint64_t old_cap = s->cap;
-    B200_CHECK(set_alloc_table(s, old_cap * 4, st));
+    B200_CHECK(set_alloc_table(s, new_cap > old_cap ? new_cap : old_cap * 4, st));
     k_set_rehash<<<nblocks(old_cap), 256, 0, st>>>(old, old_cap, s->table, s->cap - 1, old_counts, s->counts, old_slot_log, s->slot_log);
     B200_CUDA(cudaGetLastError());
     if (s->strings) { // one record per key at most: the log is as long as the table
-        B200_CUDA(cudaMalloc(&s->log, s->cap * sizeof(StrLog)));
+        s->log_bytes = s->cap * sizeof(StrLog);
+        B200_CUDA(ctx_alloc(s->ctx, reinterpret_cast<void **>(&s->log), s->log_bytes));
         if (old_log)
             B200_CUDA(cudaMemcpyAsync(s->log, old_log, old_cap * sizeof(StrLog), cudaMemcpyDeviceToDevice, st));
     }
-    B200_CUDA(cudaStreamSynchronize(st));
-    B200_CUDA(cudaFree(old));
-    if (old_counts)
-        B200_CUDA(cudaFree(old_counts));
-    if (old_slot_log)
-        B200_CUDA(cudaFree(old_slot_log));
-    if (old_log)
-        B200_CUDA(cudaFree(old_log));
+    B200_CUDA(cudaStreamSynchronize(st)); // every launch that touches a set's table runs on (or is joined to) this stream
+    ctx_release(s->ctx, old, old_cap * sizeof(SetSlot));
+    ctx_release(s->ctx, old_counts, old_cap * sizeof(unsigned long long));
+    ctx_release(s->ctx, old_slot_log, old_cap * sizeof(unsigned));
+    ctx_release(s->ctx, old_log, old_log_bytes);
     return B200_OK;
 }
 
@@ -461,7 +463,8 @@ int set_finalize(b200_set *s) {
     const size_t en = (size_t)(E ? E : 1);
     const size_t off_hist = 5 * en * 8, off_first = off_hist + align_up((size_t)256 * (nblk ? nblk : 1) * 4, 256), off_spec = off_first + align_up((size_t)s->nmaps * 8, 256);
     char *work = nullptr;
-    B200_CUDA(cudaMalloc(&work, off_spec + 256));
+    const size_t work_bytes = off_spec + 256;
+    B200_CUDA(ctx_alloc(s->ctx, reinterpret_cast<void **>(&work), work_bytes));
     unsigned long long *ckey = reinterpret_cast<unsigned long long *>(work), *tagA = ckey + en, *valA = tagA + en, *tagB = valA + en, *valB = tagB + en;
     unsigned *hist = reinterpret_cast<unsigned *>(work + off_hist);
     long long *d_first = reinterpret_cast<long long *>(work + off_first), *d_spec = reinterpret_cast<long long *>(work + off_spec);
@@ -520,18 +523,19 @@ int set_finalize(b200_set *s) {
             B200_CHECK(pass(shift, 1));
     }
     // probe table + keys in ordinal order
-    if (s->probe)
-        B200_CUDA(cudaFree(s->probe));
+    // (every reader of the previous probe table / key array holds s->mu or ran on a stream that has been synchronised since)
+    B200_CHECK(b200_ctx_sync(s->ctx, -1));
+    ctx_release(s->ctx, s->probe, s->probe_cap * sizeof(SetSlot));
     s->probe = nullptr;
-    if (s->d_keys_ord)
-        B200_CUDA(cudaFree(s->d_keys_ord));
+    ctx_release(s->ctx, s->d_keys_ord, s->keys_ord_bytes);
     s->d_keys_ord = nullptr;
     uint64_t pc = 16;
     while (pc < 2 * (n_table + 1))
         pc <<= 1;
-    B200_CUDA(cudaMalloc(&s->probe, pc * sizeof(SetSlot)));
+    B200_CUDA(ctx_alloc(s->ctx, reinterpret_cast<void **>(&s->probe), pc * sizeof(SetSlot)));
     s->probe_cap = pc;
-    B200_CUDA(cudaMalloc(&s->d_keys_ord, en * 8));
+    s->keys_ord_bytes = en * 8;
+    B200_CUDA(ctx_alloc(s->ctx, reinterpret_cast<void **>(&s->d_keys_ord), s->keys_ord_bytes));
     k_set_init<<<nblocks(pc), 256, 0, st>>>(s->probe, pc);
     B200_CUDA(cudaMemsetAsync(d_first, 0xff, (size_t)s->nmaps * 8, st)); // -1: shard without keys
     B200_CUDA(cudaMemsetAsync(d_spec, 0xff, 3 * 8, st));
@@ -543,7 +547,7 @@ int set_finalize(b200_set *s) {
     B200_CUDA(cudaMemcpyAsync(first.data(), d_first, (size_t)s->nmaps * 8, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaMemcpyAsync(spec, d_spec, sizeof spec, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
-    B200_CUDA(cudaFree(work));
+    ctx_release(s->ctx, work, work_bytes);
 
     s->n_entries = E;
     s->h_keys.clear();
@@ -613,8 +617,8 @@ int set_insert_device(b200_set *s, cudaStream_t st, const void *d_keys, const ui
         const uint64_t target = std::min<uint64_t>((known + (uint64_t)nrows) * 2, 1ull << 22);
         while (want < target)
             want <<= 1;
-        while (s->cap < want)
-            B200_CHECK(set_grow(s, st));
+        if (s->cap < want)
+            B200_CHECK(set_grow(s, st, want)); // one step (the cascade 4K -> 16K -> ... cost five allocations and rehashes)
     }
     int redo = 0;
     for (int64_t row0 = 0; row0 < nrows;) {
@@ -701,7 +705,7 @@ int b200_counter_create(b200_ctx *ctx, int dtype, int nmaps, b200_set **out) {
     b200_set *s = *out;
     s->counting = true;
     cudaStream_t st = ctx->slots[0]->stream;
-    cudaError_t e = cudaMalloc(&s->counts, s->cap * sizeof(unsigned long long));
+    cudaError_t e = ctx_alloc(s->ctx, reinterpret_cast<void **>(&s->counts), s->cap * sizeof(unsigned long long));
     if (e == cudaSuccess)
         e = cudaMemsetAsync(s->counts, 0, s->cap * sizeof(unsigned long long), st);
     if (e == cudaSuccess)
@@ -749,13 +753,15 @@ int b200_set_destroy(b200_set *s) {
     if (!s)
         return B200_OK;
     cudaSetDevice(s->ctx->device);
-    cudaFree(s->table);
-    cudaFree(s->counts);
-    cudaFree(s->probe);
-    cudaFree(s->d_keys_ord);
+    for (Slot *sl : s->ctx->slots) // the blocks go back to the cache: nothing in flight may still touch them
+        cudaStreamSynchronize(sl->stream);
+    ctx_release(s->ctx, s->table, s->cap * sizeof(SetSlot));
+    ctx_release(s->ctx, s->counts, s->cap * sizeof(unsigned long long));
+    ctx_release(s->ctx, s->probe, s->probe_cap * sizeof(SetSlot));
+    ctx_release(s->ctx, s->d_keys_ord, s->keys_ord_bytes);
     cudaFree(s->pool);
-    cudaFree(s->log);
-    cudaFree(s->slot_log);
+    ctx_release(s->ctx, s->log, s->log_bytes);
+    ctx_release(s->ctx, s->slot_log, s->cap * sizeof(unsigned));
     cudaFree(s->d_strctr);
     cudaFree(s->d_str_off);
     cudaFree(s->d_str_len);
@@ -1405,8 +1411,9 @@ int b200_strset_create(b200_ctx *ctx, int nmaps, int64_t limit, b200_set **out) 
     b200_set *s = *out;
     s->strings = true;
     cudaStream_t st = ctx->slots[0]->stream;
-    B200_CUDA(cudaMalloc(&s->slot_log, s->cap * sizeof(unsigned)));
-    B200_CUDA(cudaMalloc(&s->log, s->cap * sizeof(StrLog)));
+    B200_CUDA(ctx_alloc(s->ctx, reinterpret_cast<void **>(&s->slot_log), s->cap * sizeof(unsigned)));
+    s->log_bytes = s->cap * sizeof(StrLog);
+    B200_CUDA(ctx_alloc(s->ctx, reinterpret_cast<void **>(&s->log), s->log_bytes));
     B200_CUDA(cudaMalloc(&s->d_strctr, 16));
     B200_CUDA(cudaMemsetAsync(s->d_strctr, 0, 16, st));
     B200_CUDA(cudaStreamSynchronize(st));
@@ -1438,8 +1445,8 @@ int b200_strset_update(b200_set *s, int slot, const int64_t *offsets, const uint
         const uint64_t target = std::min<uint64_t>((known + (uint64_t)nrows) * 2, 1ull << 22);
         while (want < target)
             want <<= 1;
-        while (s->cap < want)
-            B200_CHECK(set_grow(s, st));
+        if (s->cap < want)
+            B200_CHECK(set_grow(s, st, want)); // one step (the cascade 4K -> 16K -> ... cost five allocations and rehashes)
         unsigned long long sc[2];
         B200_CUDA(cudaMemcpyAsync(sc, s->d_strctr, 16, cudaMemcpyDeviceToHost, st));
         B200_CUDA(cudaStreamSynchronize(st));

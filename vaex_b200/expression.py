@@ -7,7 +7,7 @@ ONCE from its Python AST into a postfix program for ``b200_eval`` (csrc/expr.cu)
 compiler asks numpy itself (zero-length arrays, so NEP 50's weak Python scalars are honoured) — and the device performs exactly one
 correctly rounded operation per node in that dtype, which makes the results bit-identical to the reference's numpy evaluation.
 
-Supported: column names, numeric literals, ``+ - * /``, unary ``-``, ``abs() sqrt()``, ``< <= > >= == !=`` (also chained), ``& | ~``
+Supported: column names, numeric literals, ``+ - * /``, unary ``-``, ``abs() sqrt()``, ``< <= > >= == !=`` (not chained: numpy rejects `a < b < c` on arrays too), ``& | ~``
 on booleans, ``.astype('dtype')`` and ``_ordinal_values(x, hash_map_unique)`` (vaex/functions.py:2454-2463).  Anything else raises
 ``NotImplementedError`` when the expression is compiled — never a silent CPU evaluation.
 """
