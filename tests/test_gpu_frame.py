@@ -139,7 +139,7 @@ def test_task_merging_single_pass():
 
 
 @pytest.mark.parametrize("fused", [True, False])
-def test_groupby_sum_count(fused):
+def test_groupby_sum_count(fused, oracle):
     # tests/groupby_test.py:116-176 style: groupby over hashed int64 keys, sum + count, against numpy
     from vaex_b200.frame import Frame
     rng = np.random.default_rng(4)
@@ -155,9 +155,13 @@ def test_groupby_sum_count(fused):
     np.testing.assert_array_equal(np.asarray(out["k"])[order], uniq)
     np.testing.assert_array_equal(out["v_count"][order], want_cnt)
     np.testing.assert_allclose(out["v_sum"][order], want_sum, rtol=1e-9, atol=1e-9)
-    # first-seen order, like the sequential reference
-    first_seen = keys[np.sort(np.unique(keys, return_index=True)[1])]
-    assert set(out["k"].tolist()) == set(first_seen.tolist())
+    # group order == the ordinals of the sequential reference: ordered_set with 7 shards (vaex/cpu.py:317), keys in
+    # key_array() order (shard by shard, insertion order inside a shard: src/hash.hpp:337-353), restated by the oracle
+    ref = oracle.OrderedSet("int64", 7)
+    ref.update(keys, None, -1, False)
+    assert np.array_equal(np.asarray(out["k"]), ref.key_array())
+    ordinals = ref.map_ordinal(keys)
+    np.testing.assert_array_equal(out["v_count"], np.bincount(ordinals, minlength=len(ref)))
 
 
 def test_groupby_float_keys_nan_and_missing():

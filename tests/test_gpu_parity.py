@@ -343,3 +343,29 @@ def test_bin_index_sweep_all_fp32(oracle):
             assert np.array_equal(w.sum(axis=axis), got_x)
             total += got.sum()
     assert int(total) == 1 << 32
+
+
+def test_ring_partition_more_than_one_batch_is_linear():
+    """More than 2^30 rows in ONE call: csrc/ringcount.cu cuts the call into equal batches (32-bit entry counts).  Size-independent
+    property instead of a 9 GB host oracle pass: the grid of the whole call equals the sum of the grids of two calls that each fit
+    one batch, and the grid's total equals the row count."""
+    import torch
+    from vaex_b200 import superagg
+    n = (1 << 30) + 77_777
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.empty(n, dtype=torch.float32, device="cuda").normal_(generator=gen)
+    y = torch.empty(n, dtype=torch.float32, device="cuda").normal_(generator=gen)
+    bx = superagg.BinnerScalar_float32(1, "x", -3, 3, 1024)
+    by = superagg.BinnerScalar_float32(1, "y", -3, 3, 1024)
+    grid = superagg.Grid([bx, by])
+
+    def count(lo, hi):
+        agg = superagg.AggCount_int64(grid, 1, 1)
+        bx.set_data(0, x[lo:hi])
+        by.set_data(0, y[lo:hi])
+        grid.bin(0, [agg], hi - lo)
+        return agg.get_result()
+    whole = count(0, n)
+    cut = 600_000_003
+    parts = count(0, cut) + count(cut, n)
+    assert int(whole.sum()) == n and np.array_equal(whole, parts)
