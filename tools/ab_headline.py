@@ -50,7 +50,7 @@ def main():
     import hashlib
     sha = hashlib.sha1(res.tobytes()).hexdigest()[:16]
     times.sort()
-    print(json.dumps({"tag": args.tag, "lib": os.path.basename(_lib.LIB_PATH), "path": os.environ.get("B200_COUNT_PATH", "ring"), "fg": os.environ.get("B200_RING_FG"), "rows": n,
+    print(json.dumps({"tag": args.tag, "lib": os.path.basename(_lib.LIB_PATH), "path": "ring", "fg": os.environ.get("B200_RING_FG"), "rows": n,
                       "ms_min": times[0], "ms_median": times[len(times) // 2], "rows_per_s_median": n / (times[len(times) // 2] * 1e-3), "count_ok": total == n, "grid_sha": sha}))
 
 

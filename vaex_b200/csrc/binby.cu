@@ -251,7 +251,6 @@ int launch_variant(b200_ctx *ctx, cudaStream_t stream, const BinParams &p) {
 } // namespace
 
 int try_launch_fast(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool vec, bool *taken);          // fast.cu
-int try_launch_tilecount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool vec, bool *taken);     // tilecount.cu (round 1)
 int try_launch_ringcount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool vec, bool *taken);     // ringcount.cu
 
 int launch_binby(b200_ctx *ctx, Slot *slot, const BinParams &p, bool vec) {
@@ -266,12 +265,7 @@ int launch_binby(b200_ctx *ctx, Slot *slot, const BinParams &p, bool vec) {
     static const bool disable_fast = getenv("B200_DISABLE_FAST") && atoi(getenv("B200_DISABLE_FAST")) != 0;
     if (!disable_fast) {
         bool taken = false;
-        // B200_COUNT_PATH=tile: round 1's sort-by-tile kernel pair (kept for A/B timing on one box)
-        static const bool use_tile = getenv("B200_COUNT_PATH") && !strcmp(getenv("B200_COUNT_PATH"), "tile");
-        if (use_tile)
-            B200_CHECK(try_launch_tilecount(ctx, slot, p, vec, &taken));
-        else
-            B200_CHECK(try_launch_ringcount(ctx, slot, p, vec, &taken));
+        B200_CHECK(try_launch_ringcount(ctx, slot, p, vec, &taken));
         if (taken)
             return B200_OK;
         B200_CHECK(try_launch_fast(ctx, slot, p, vec, &taken));

@@ -590,7 +590,7 @@ bool magic_exact(unsigned cells, unsigned tile_cells, unsigned magic) {
 // Scratch (pool + list tables) lives in the slot; grown on demand.
 int try_launch_ringcount(b200_ctx *ctx, Slot *slot, const BinParams &bp, bool vec, bool *taken) {
     *taken = false;
-    static const bool disabled = getenv("B200_DISABLE_TILECOUNT") && atoi(getenv("B200_DISABLE_TILECOUNT")) != 0;
+    static const bool disabled = getenv("B200_DISABLE_RINGCOUNT") && atoi(getenv("B200_DISABLE_RINGCOUNT")) != 0;
     static const bool no_clamp = getenv("B200_RING_NO_CLAMP") && atoi(getenv("B200_RING_NO_CLAMP")) != 0; // A/B knob
     if (disabled || !vec || bp.nb < 1 || bp.nb > 3 || bp.na != 1 || bp.nrows < (1ll << 22))
         return B200_OK;

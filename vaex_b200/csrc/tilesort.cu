@@ -4,7 +4,7 @@
 // With direct scatter every row touches up to three random 32-byte sectors of HBM (fill + write-back).  Packing the three
 // accumulators of a cell into one 32-byte record (the round's earlier "interleaved record" variant) brought that to one sector
 // and still ran at ~1.5 TB/s of random sector traffic: 43.6 ms per 1e9 rows (profiles/r01_bench_configs.txt).  Here the rows of a batch are first SORTED BY GRID REGION (k_sort_partition: the same
-// warp-autonomous counting sort as tilecount.cu, carrying {cell index u32, value f64} = 12 bytes per row), and the regions are
+// warp-autonomous counting sort as round 1's headline kernel used (tilecount.cu, since replaced by ringcount.cu), carrying {cell index u32, value f64} = 12 bytes per row), and the regions are
 // then applied one after another (k_sort_apply) — the part of the grids a region covers is <= 32 MB and stays in the 126 MB
 // L2, so the REDs never go to HBM and the pass is bound by the L2 request rate (~98 REDs/clk, profiles/r01_microbench.txt)
 // instead of random DRAM sectors.
@@ -86,7 +86,7 @@ __host__ __device__ constexpr size_t warp_bytes() {
 
 template <typename T, int ND, typename TV, bool HASV, int PPL>
 __global__ void __launch_bounds__(kWarps * 32, 2) k_sort_partition(const __grid_constant__ SortParams p) {
-    // every warp is autonomous (see tilecount.cu: k_tile_partition): sort 512 rows by region in shared memory, append each
+    // every warp is autonomous: sort 512 rows by region in shared memory, append each
     // segment to the region's bucket inside a chunk of kChunk entries the warp owns
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
