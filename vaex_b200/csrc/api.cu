@@ -261,42 +261,37 @@ static int agg_fill(b200_agg *a, cudaStream_t st) {
     if (a->op == B200_AGG_FIRST || a->op == B200_AGG_LAST) {
         // src/agg_first.cpp:19-26: value 99, order limits, cell_masked 1; the packed {key,row} state starts at the maximum
         const int isz = dtype_size(a->dtype), isz2 = dtype_size(a->dtype2);
-        std::vector<unsigned char> v((size_t)a->cells * isz), o((size_t)a->cells * isz2);
         const bool inv = a->op == B200_AGG_LAST;
-        for (uint64_t i = 0; i < a->cells; i++) {
-            switch (a->dtype) {
-            case B200_F64: reinterpret_cast<double *>(v.data())[i] = 99; break;
-            case B200_F32: reinterpret_cast<float *>(v.data())[i] = 99; break;
-            case B200_BOOL: v[i] = 1; break;
-            default:
-                if (isz == 8)
-                    reinterpret_cast<uint64_t *>(v.data())[i] = 99;
-                else if (isz == 4)
-                    reinterpret_cast<uint32_t *>(v.data())[i] = 99;
-                else if (isz == 2)
-                    reinterpret_cast<uint16_t *>(v.data())[i] = 99;
-                else
-                    v[i] = 99;
-            }
-            switch (a->dtype2) {
-            case B200_F64: reinterpret_cast<double *>(o.data())[i] = inv ? 2.2250738585072014e-308 : 1.7976931348623157e308; break;
-            case B200_F32: reinterpret_cast<float *>(o.data())[i] = inv ? 1.17549435e-38f : 3.40282347e38f; break;
-            case B200_I64: reinterpret_cast<int64_t *>(o.data())[i] = inv ? INT64_MIN : INT64_MAX; break;
-            case B200_I32: reinterpret_cast<int32_t *>(o.data())[i] = inv ? INT32_MIN : INT32_MAX; break;
-            case B200_I16: reinterpret_cast<int16_t *>(o.data())[i] = inv ? INT16_MIN : INT16_MAX; break;
-            case B200_I8: reinterpret_cast<int8_t *>(o.data())[i] = inv ? INT8_MIN : INT8_MAX; break;
-            case B200_U64: reinterpret_cast<uint64_t *>(o.data())[i] = inv ? 0 : UINT64_MAX; break;
-            case B200_U32: reinterpret_cast<uint32_t *>(o.data())[i] = inv ? 0 : UINT32_MAX; break;
-            case B200_U16: reinterpret_cast<uint16_t *>(o.data())[i] = inv ? 0 : UINT16_MAX; break;
-            case B200_U8: o[i] = inv ? 0 : UINT8_MAX; break;
-            default: o[i] = inv ? 0 : 1; break;
-            }
+        auto bits_of = [](auto x) {
+            uint64_t b = 0;
+            memcpy(&b, &x, sizeof x);
+            return b;
+        };
+        uint64_t vbits = 99, obits = 0;
+        switch (a->dtype) {
+        case B200_F64: vbits = bits_of(99.0); break;
+        case B200_F32: vbits = bits_of(99.0f); break;
+        case B200_BOOL: vbits = 1; break;
+        default: break;
         }
-        B200_CUDA(cudaMemcpyAsync(a->grid, v.data(), v.size(), cudaMemcpyHostToDevice, st));
-        B200_CUDA(cudaMemcpyAsync(a->order, o.data(), o.size(), cudaMemcpyHostToDevice, st));
+        switch (a->dtype2) {
+        case B200_F64: obits = bits_of(inv ? 2.2250738585072014e-308 : 1.7976931348623157e308); break;
+        case B200_F32: obits = bits_of(inv ? 1.17549435e-38f : 3.40282347e38f); break;
+        case B200_I64: obits = (uint64_t)(inv ? INT64_MIN : INT64_MAX); break;
+        case B200_I32: obits = (uint32_t)(inv ? INT32_MIN : INT32_MAX); break;
+        case B200_I16: obits = (uint16_t)(inv ? INT16_MIN : INT16_MAX); break;
+        case B200_I8: obits = (uint8_t)(inv ? INT8_MIN : INT8_MAX); break;
+        case B200_U64: obits = inv ? 0 : UINT64_MAX; break;
+        case B200_U32: obits = inv ? 0 : UINT32_MAX; break;
+        case B200_U16: obits = inv ? 0 : UINT16_MAX; break;
+        case B200_U8: obits = inv ? 0 : UINT8_MAX; break;
+        default: obits = inv ? 0 : 1; break;
+        }
+        // filled on the device, stream-ordered: no O(cells) host vectors, no host sync
+        B200_CHECK(launch_fill_elems(st, a->grid, isz, a->cells, vbits));
+        B200_CHECK(launch_fill_elems(st, a->order, isz2, a->cells, obits));
         B200_CUDA(cudaMemsetAsync(a->cell_masked, 1, a->cells, st));
         B200_CUDA(cudaMemsetAsync(a->state, 0xff, a->cells * 16, st));
-        B200_CUDA(cudaStreamSynchronize(st)); // the host vectors die at scope exit
         return B200_OK;
     }
     const uint64_t bits = agg_init_bits(a->op, a->cell_dtype);

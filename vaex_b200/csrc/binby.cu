@@ -199,6 +199,10 @@ __global__ void k_fill32(unsigned *p, uint64_t n, unsigned v) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
         p[i] = v;
 }
+__global__ void k_fill16(unsigned short *p, uint64_t n, unsigned short v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
 
 // Aggregator::merge (src/agg_count.cpp:15-23, src/agg_sum.cpp:69-76, src/agg_minmax.cpp:19-27)
 __global__ void k_merge(int op, int cell_dtype, void *dst, const void *src, uint64_t n) {
@@ -285,6 +289,21 @@ int launch_fill(cudaStream_t stream, void *ptr, int cell_dtype, uint64_t cells, 
         k_fill64<<<blocks, 256, 0, stream>>>(static_cast<unsigned long long *>(ptr), cells, bits);
     else
         k_fill32<<<blocks, 256, 0, stream>>>(static_cast<unsigned *>(ptr), cells, (unsigned)bits);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
+// n elements of `isz` bytes (1, 2, 4 or 8), each set to the low bytes of `bits`
+int launch_fill_elems(cudaStream_t stream, void *ptr, int isz, uint64_t n, uint64_t bits) {
+    if (!n)
+        return B200_OK;
+    const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    switch (isz) {
+    case 8: k_fill64<<<blocks, 256, 0, stream>>>(static_cast<unsigned long long *>(ptr), n, bits); break;
+    case 4: k_fill32<<<blocks, 256, 0, stream>>>(static_cast<unsigned *>(ptr), n, (unsigned)bits); break;
+    case 2: k_fill16<<<blocks, 256, 0, stream>>>(static_cast<unsigned short *>(ptr), n, (unsigned short)bits); break;
+    default: B200_CUDA(cudaMemsetAsync(ptr, (int)(bits & 0xff), n, stream)); break;
+    }
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }

@@ -101,6 +101,7 @@ int launch_nunique(b200_ctx *ctx, cudaStream_t stream, const NUniqueParams &p, b
 int launch_nunique_rehash(cudaStream_t stream, const unsigned long long *old_table, unsigned long long old_cap, unsigned long long *table, unsigned long long cap);
 int launch_first(b200_ctx *ctx, cudaStream_t stream, const FirstParams &p, bool vec);
 int launch_fill(cudaStream_t stream, void *ptr, int cell_dtype, uint64_t cells, uint64_t bits);
+int launch_fill_elems(cudaStream_t stream, void *ptr, int isz, uint64_t n, uint64_t bits);
 int launch_merge(cudaStream_t stream, int op, int cell_dtype, void *dst, const void *src, uint64_t cells);
 int launch_merge_first(cudaStream_t stream, b200_agg *dst, const b200_agg *src);
 

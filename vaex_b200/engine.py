@@ -76,14 +76,13 @@ _SIGN = -(1 << 63)
 def all_reduce_first_tensors(key, row, value, order, masked, group=None):
     """first/last across row shards: every rank holds, per cell, the packed winner of ITS rows — `key` (the order
     key as u64 bits, smaller wins; LAST stores the complement), `row` (global row index, the tie-break), the winner's `value`
-    and `order` bits (int64 tensors) and `masked` (1 = no row of this rank fell into the cell).  Three MIN all-reduces find
-    the global (key, row) winner, which exactly one rank owns (rows are globally unique); that rank alone contributes its
-    value / order bits to two SUM all-reduces.  All tensors are updated in place; works on any backend (gloo in the CPU test)."""
+    and `order` bits (int64 tensors) and `masked` (1 = no row of this rank fell into the cell).  THREE all-reduces: MIN over the
+    keys, MIN over the rows of the ranks that hold that key — together the global (key, row) winner, which exactly one rank owns
+    (rows are globally unique) — and one SUM over the stacked [value bits, order bits, has-a-row flag] to which only the owner
+    contributes its bits.  All tensors are updated in place; works on any backend (gloo in the CPU test)."""
     import torch
     import torch.distributed as dist
     imax = torch.iinfo(torch.int64).max
-    gmask = masked.to(torch.int32)
-    dist.all_reduce(gmask, op=dist.ReduceOp.MIN, group=group)
     has = masked == 0
     k = torch.where(has, key ^ _SIGN, torch.full_like(key, imax))  # u64 order through a signed view: flip the sign bit
     gk = k.clone()
@@ -92,16 +91,14 @@ def all_reduce_first_tensors(key, row, value, order, masked, group=None):
     gr = r.clone()
     dist.all_reduce(gr, op=dist.ReduceOp.MIN, group=group)
     owner = has & (k == gk) & (r == gr)
-    gv = torch.where(owner, value, torch.zeros_like(value))
-    go = torch.where(owner, order, torch.zeros_like(order))
-    dist.all_reduce(gv, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(go, op=dist.ReduceOp.SUM, group=group)
-    any_has = gmask == 0
+    packed = torch.stack([torch.where(owner, value, torch.zeros_like(value)), torch.where(owner, order, torch.zeros_like(order)), has.to(torch.int64)])
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    any_has = packed[2] > 0
     key.copy_(torch.where(any_has, gk ^ _SIGN, key))
     row.copy_(torch.where(any_has, gr, row))
-    value.copy_(torch.where(any_has, gv, value))
-    order.copy_(torch.where(any_has, go, order))
-    masked.copy_(gmask.to(masked.dtype))
+    value.copy_(torch.where(any_has, packed[0], value))
+    order.copy_(torch.where(any_has, packed[1], order))
+    masked.copy_((~any_has).to(masked.dtype))
 
 
 def _raw_tensor(agg, which, np_dtype):
