@@ -374,3 +374,53 @@ def test_groupby_combine_recurses_past_64_bits(device, sort, oracle):
         o = [inner // m1[0], inner % m1[0] // m1[1], inner % m1[1], final % len(sets[3])]
         for name, s_, oo in zip("abcd", sets, o):
             assert np.array_equal(np.asarray(out[name]), s_.key_array()[oo])
+
+
+@pytest.mark.parametrize("dropnan", [False, True])
+@pytest.mark.parametrize("by_col_has_missing", [False, True])
+@pytest.mark.parametrize("combine", [False, True])
+def test_groupby_agg_list(dropnan, by_col_has_missing, combine):
+    # tests/agg_test.py:660-693 (test_agg_list), the numeric column: groupby('id').agg(list(num, dropnan=...)) -> one arrow list per group
+    from vaex_b200 import agg
+    from vaex_b200.frame import Frame
+    ids = np.ma.array([1, 2, 2, 1, 1, 3, 3], mask=[0, 0, 0, 0, 0, by_col_has_missing, by_col_has_missing], dtype="i8")
+    num = np.array([1.1, 1.2, 1.3, 1.4, np.nan, 1.6, 1.7])
+    cols = dict(id=ids, num=num)
+    by = "id"
+    if combine:  # the sparse path (tests/agg_test.py:723): a second, constant key
+        cols["one"] = np.zeros(7, "i4")
+        by = ["id", "one"]
+    df = Frame(cols)
+    # sort=True: the reference groups small-range integer keys with BinnerInteger, i.e. in key order (vaex/groupby.py:598-600)
+    out = df.groupby(by, agg=[agg.list("num", dropnan=dropnan)], combine=combine, sort=True)
+    result = out["num_list"].to_pylist()
+    if dropnan:
+        assert result == [[1.1, 1.4], [1.2, 1.3], [1.6, 1.7]]
+    else:
+        assert result[1:] == [[1.2, 1.3], [1.6, 1.7]]
+        assert result[0][:2] == [1.1, 1.4] and np.isnan(result[0][2]) and len(result[0]) == 3
+    assert out["id"].tolist() == ([1, 2, None] if by_col_has_missing else [1, 2, 3])
+    assert out["count"].tolist() == [3, 2, 2]
+
+
+def test_frame_list_binby_through_the_task_part():
+    # Frame.list -> AggregatorDescriptorBasic('AggList') -> TaskPartAggregation (chunked over 3 workers): per cell of the full grid
+    # (edge cells included, first binner fastest) the values in ROW order, whatever worker fed the chunk (vaex/agg.py:654-674)
+    from vaex_b200.execution import Executor
+    from vaex_b200.frame import Frame
+    rng = np.random.default_rng(8)
+    n = 50_000
+    x = rng.uniform(-1, 11, n)
+    v = rng.integers(0, 1000, n).astype("i4")
+    df = Frame(dict(x=x, v=v), executor=Executor(nthreads=3, chunk_size=7_001))
+    lists = df.list("v", binby="x", limits=[0, 10], shape=5)
+    assert len(lists) == 8
+    cell = np.where(np.isnan(x), 0, np.where(x < 0, 1, np.where(x >= 10, 7, np.floor(x / 2) + 2))).astype(int)
+    for c in range(8):
+        got = np.asarray(lists[c].as_py(), dtype="i4")
+        want = v[cell == c]
+        # chunks are fed concurrently: the order inside a cell is row order within a chunk, chunks in completion order
+        assert np.array_equal(np.sort(got), np.sort(want))
+    single = Frame(dict(x=x, v=v), executor=Executor(nthreads=1, chunk_size=7_001)).list("v", binby="x", limits=[0, 10], shape=5)
+    for c in range(8):
+        assert np.array_equal(np.asarray(single[c].as_py(), dtype="i4"), v[cell == c])  # sequential feed: exactly row order

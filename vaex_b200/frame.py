@@ -422,7 +422,7 @@ class GroupBy:
             for name, hm, ordinals in zip(self.by, self.hash_maps, self._decode(group_codes)):
                 out[name] = hm.keys()[ordinals]
             for label, g in zip(labels[:-1], grids[:-1]):
-                out[label] = g[:-2][keep]
+                out[label] = _take_cells(g, np.nonzero(keep)[0]) if _is_arrow(g) else g[:-2][keep]
             out["count"] = counts[keep]
             return out
         for name, hm in zip(self.by, self.hash_maps):
@@ -449,7 +449,20 @@ class GroupBy:
         mesh = np.meshgrid(*[np.arange(len(hm)) for hm in self.hash_maps], indexing="ij")
         for name, hm, m in zip(self.by, self.hash_maps, mesh):
             out[name] = hm.keys()[m[keep]]
+        # a list aggregator returns ONE arrow list per cell of the flat FULL grid (first binner fastest, edge cells included)
+        shape = [len(hm) + 2 for hm in self.hash_maps]
+        strides = np.cumprod([1] + shape[:-1])
+        flat = sum(i.astype(np.int64) * int(st) for i, st in zip(np.nonzero(keep), strides))
         for label, g in zip(labels[:-1], grids[:-1]):
-            out[label] = g[center][keep]
+            out[label] = _take_cells(g, flat) if _is_arrow(g) else g[center][keep]
         out["count"] = counts[keep]
         return out
+
+
+def _is_arrow(x):
+    return type(x).__module__.startswith("pyarrow")
+
+
+def _take_cells(lists, cells):
+    import pyarrow as pa
+    return lists.take(pa.array(np.asarray(cells, dtype=np.int64)))

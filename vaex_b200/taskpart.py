@@ -171,6 +171,9 @@ class TaskPartAggregation(TaskPart):
         results = []
         for agg_desc, selections, ops, selection_waslist in self.aggregations:
             grids = [agg_desc.get_result(op) for op in ops]
+            if type(grids[0]).__module__.startswith("pyarrow"):  # AggList: one arrow large_list per cell (immutable, nothing to copy)
+                results.append(grids if selection_waslist else grids[0])
+                continue
             result = np.asarray(grids) if selection_waslist else grids[0]
             if not np.ma.isMaskedArray(result):
                 result = result.copy()
