@@ -19,6 +19,9 @@ def main():
     ap.add_argument("--rows", type=float, default=1e9)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--occupy", default="", help="CTAS,MICROSECONDS: a do-nothing kernel holding that many SMs (1024 threads, 200 KB of shared memory "
+                                                "each) is released on another slot's stream at the moment the timed pass starts — what an NCCL all-reduce of "
+                                                "the previous step does to the partition kernel on a multi-GPU run")
     args = ap.parse_args()
     import torch
     from vaex_b200 import _lib, engine, superagg
@@ -40,6 +43,10 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record()
+            if args.occupy:
+                ctas, usec = (int(v) for v in args.occupy.split(","))
+                engine.slot_stream(ctx, 1).wait_event(e0)
+                _lib.check(_lib.lib().b200_ctx_occupy(ctx._h, 1, ctas, 1024, 200 * 1024, usec * 1000))
             grid.bin(0, [agg], n)
             e1.record()
         ctx.sync()
@@ -50,7 +57,7 @@ def main():
     import hashlib
     sha = hashlib.sha1(res.tobytes()).hexdigest()[:16]
     times.sort()
-    print(json.dumps({"tag": args.tag, "lib": os.path.basename(_lib.LIB_PATH), "path": "ring", "fg": os.environ.get("B200_RING_FG"), "rows": n,
+    print(json.dumps({"tag": args.tag, "lib": os.path.basename(_lib.LIB_PATH), "path": "ring", "fg": os.environ.get("B200_RING_FG"), "rows": n, "occupy": args.occupy or None,
                       "ms_min": times[0], "ms_median": times[len(times) // 2], "rows_per_s_median": n / (times[len(times) // 2] * 1e-3), "count_ok": total == n, "grid_sha": sha}))
 
 

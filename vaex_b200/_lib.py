@@ -105,6 +105,7 @@ def lib():
             "b200_ctx_stream": (i32, [vp, i32, P(vp)]),
             "b200_ctx_path_stats": (i32, [vp, i32, P(u64)]),
             "b200_ctx_host_stats": (i32, [vp, P(u64), i32]),
+            "b200_ctx_occupy": (i32, [vp, i32, i32, i32, i32, u64]),
             "b200_agg_create": (i32, [vp, i32, i32, i32, i32, u32, u64, P(vp)]),
             "b200_agg_destroy": (i32, [vp]),
             "b200_agg_reset": (i32, [vp]),

@@ -469,6 +469,34 @@ int b200_ctx_path_stats(b200_ctx *ctx, int slot, uint64_t out[6]) {
     return B200_OK;
 }
 
+namespace {
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void k_spin(unsigned long long ns) {
+    extern __shared__ unsigned char spin_smem[];
+    const unsigned long long t0 = globaltimer_ns();
+    while (globaltimer_ns() - t0 < ns)
+        __nanosleep(200);
+    if (ns == ~0ull)
+        spin_smem[threadIdx.x] = 0;
+}
+} // namespace
+
+int b200_ctx_occupy(b200_ctx *ctx, int slot, int ctas, int threads, int smem_bytes, uint64_t nanoseconds) {
+    if (!ctx || slot < 0 || slot >= ctx->nslots || ctas < 1 || threads < 1 || threads > 1024 || smem_bytes < 0) {
+        set_error("b200_ctx_occupy: invalid argument");
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(ctx->device));
+    B200_CUDA(cudaFuncSetAttribute(k_spin, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    k_spin<<<ctas, threads, smem_bytes, ctx->slots[slot]->stream>>>(nanoseconds);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
 int b200_ctx_host_stats(b200_ctx *ctx, uint64_t out[6], int reset) {
     if (!ctx || !out) {
         set_error("b200_ctx_host_stats: invalid argument");
