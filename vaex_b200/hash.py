@@ -142,8 +142,24 @@ class HashMapUnique:
 
     def sorted(self, ascending=True, return_keys=False):
         if self.is_string:
-            raise NotImplementedError("sorted string key sets are not supported: sort the result by key instead")
+            return self._sorted_strings(ascending, return_keys)
         return self._sorted(ascending, return_keys)
+
+    def _sorted_strings(self, ascending=True, return_keys=False):
+        # vaex/hash.py:246-268 for string keys: arrow's (bytewise) order, the null key last; the sorted keys go into a fresh 1-shard
+        # device set in that order, so ordinal == rank
+        import pyarrow as pa
+        import pyarrow.compute as pc
+        keys = self._internal.key_array()
+        valid = pc.drop_null(keys)
+        sorted_keys = valid.take(pc.array_sort_indices(valid, order="ascending" if ascending else "descending"))
+        if self.has_null:
+            sorted_keys = pa.concat_arrays([sorted_keys, pa.array([None], type=sorted_keys.type)])
+        internal = type(self._internal)(1)
+        if len(sorted_keys):
+            internal.update(sorted_keys)
+        out = HashMapUnique(self.dtype, _internal=internal)
+        return (out, np.array(sorted_keys.to_pylist(), dtype=object)) if return_keys else out
 
     def _sorted(self, ascending=True, return_keys=False):
         # vaex/hash.py:246-268 — arrow sorts nulls last; NaN sorts after every number
