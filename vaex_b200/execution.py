@@ -194,8 +194,8 @@ def merge_aggregation_tasks(requests, dtypes, nthreads):
         selections = []
         for d, s in zip(descs, sels):
             d_sel = d.selection if isinstance(d.selection, (list, tuple)) else [d.selection]
-            for one in d_sel:
-                selections.append(None if one is None or one is False else s)
+            for i, one in enumerate(d_sel):
+                selections.append(None if one is None or one is False else (s[i] if isinstance(s, (list, tuple)) else s))
         tasks.append(Task(part, selections))
     pos = {}
     for binner_specs, desc, sel in requests:

@@ -194,15 +194,25 @@ class Frame:
         aggregators = [aggregators] if single else list(aggregators)
         specs = self._binner_specs(binby, limits, shape)
         dtypes = self.dtypes()
-        if isinstance(selection, str):  # a selection expression: a boolean mask evaluated on the device per chunk
-            selection = self.expression(selection)
-            if selection.dtype != np.bool_:
-                raise ValueError("a selection must be a boolean expression")
+        def as_mask(one):
+            if isinstance(one, str):  # a selection expression: a boolean mask evaluated on the device per chunk
+                one = self.expression(one)
+                if one.dtype != np.bool_:
+                    raise ValueError("a selection must be a boolean expression")
+            return one
+        # a LIST of selections gives one grid per selection, stacked along a new first axis (vaex/cpu.py:744-786, :798-811)
+        if isinstance(selection, (list, tuple)):
+            selection = [None if one is None or one is False else as_mask(one) for one in selection]
+        else:
+            selection = as_mask(selection)
         requests = []
         for a in aggregators:
             for prim in a.primitives():
                 prim.edges = edges or prim.edges
-                prim.selection = None if selection is None else "selection"
+                if isinstance(selection, list):
+                    prim.selection = [None if one is None else f"selection{i}" for i, one in enumerate(selection)]
+                else:
+                    prim.selection = None if selection is None else "selection"
                 requests.append((specs, prim, selection))
         tasks, pos = execution.merge_aggregation_tasks(requests, dtypes, self.executor.nthreads)
         self.executor.execute(self.columns, tasks, self.length, filter=self._filter, progress=progress)
@@ -274,6 +284,16 @@ class Frame:
         count; NaN / missing get their own entries unless dropped."""
         from . import superutils
         col = self.columns[expression]
+        if _hash.is_string_column(col):
+            # string keys: the device string set + a count per ordinal (the reference counts with counter<string>, vaex/cpu.py:141-283)
+            out = self.groupby(expression, agg=[_agg.count()])
+            keys, counts = np.asarray(out[expression], dtype=object), np.asarray(out["count"])
+            if dropna or dropmissing:
+                keep = np.array([k is not None for k in keys], dtype=bool)
+                keys, counts = keys[keep], counts[keep]
+            order = np.argsort(counts, kind="stable")
+            order = order if ascending else order[::-1]
+            return keys[order], counts[order]
         dt = _dtype_of(col)
         counter = getattr(superutils, "counter_" + np.dtype(dt).newbyteorder("=").name)(1)
         chunk = self.executor.chunk_size_for(self.length) if not _is_device(col) else max(self.length, 1)
