@@ -85,3 +85,17 @@ def test_groupby_count_nunique_on_string_columns():
         for drop in (False, True):
             nu = df.nunique(name, binby=["g"], dropmissing=drop)
             assert nu.tolist() == [ref_nunique(col, b, drop) for b in range(5)], (name, drop)
+
+
+def test_string_set_pickle_round_trip():
+    # vaex/hash.py:28-36: ordered_set_string pickles as (keys in ordinal order, null_index, ...) and comes back with the same ordinals
+    import pickle
+    import pyarrow as pa
+    from vaex_b200 import superutils
+    words = ["noot", "aap", None, "mies", "aap", "", "noot", "kees"]
+    s = superutils.ordered_set_string(3)
+    s.update(pa.array(words))
+    t = pickle.loads(pickle.dumps(s))
+    assert t.keys() == s.keys() and t.null_count == s.null_count and len(t) == len(s)
+    probe = pa.array(["kees", "aap", "xx", None, ""])
+    assert np.array_equal(np.asarray(t.map_ordinal(probe)), np.asarray(s.map_ordinal(probe)))

@@ -416,3 +416,20 @@ class ordered_set_string:
         out = np.zeros(self.nmaps, np.int64)
         _lib.check(_lib.lib().b200_set_offsets(self._h, out.ctypes.data))
         return out.tolist()
+
+
+def create_set_string(keys, null_index=-1, nan_count=0, null_count=0, fingerprint=""):
+    """vaex/hash.py:28-36: an ordered_set_string rebuilt from its keys in ordinal order (a pyarrow string array whose null slot, if
+    any, is the null key) — one shard, so ordinal == position again."""
+    s = ordered_set_string(1)
+    if len(keys):
+        s.update(keys)
+    s.fingerprint = fingerprint
+    return s
+
+
+def _pickle_set_string(x):
+    return create_set_string, (x.key_array(), x.null_index, 0, x.null_count, x.fingerprint)
+
+
+copyreg.pickle(ordered_set_string, _pickle_set_string)
