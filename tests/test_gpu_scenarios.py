@@ -100,3 +100,24 @@ def test_count_with_a_list_of_selections():
     edge_all, edge_sel = int((y == 2).sum()), int(((y == 2) & (x > 0)).sum())  # numpy closes the last bin, the reference does not
     assert np.array_equal(np.asarray(both)[0], h_all - np.eye(8, dtype=int)[-1] * edge_all)
     assert np.array_equal(np.asarray(both)[1], h_sel - np.eye(8, dtype=int)[-1] * edge_sel)
+
+
+def test_groupby_agg_argument_forms():
+    # tests/groupby_test.py:15-33, 56-80: agg='count', {'label': descriptor}, {column: descriptor}, {column: [names]}
+    from vaex_b200 import agg
+    rng = np.random.default_rng(9)
+    n = 8000
+    g = rng.integers(0, 5, n).astype("i8")
+    x = rng.normal(0, 1, n)
+    df = _frame(g=g, x=x)
+    counts = np.bincount(g)
+    out = df.groupby("g", agg="count", sort=True)
+    assert out["count"].tolist() == counts.tolist()
+    out = df.groupby("g", agg={"mean_x": agg.mean("x"), "biggest": agg.max("x")}, sort=True)
+    np.testing.assert_allclose(out["mean_x"], [x[g == k].mean() for k in range(5)], rtol=1e-12)
+    assert out["biggest"].tolist() == [x[g == k].max() for k in range(5)]
+    out = df.groupby("g", agg={"x": agg.std("x")}, sort=True)
+    np.testing.assert_allclose(out["x"], [x[g == k].std() for k in range(5)], rtol=1e-9)
+    out = df.groupby("g", agg={"x": ["min", agg.sum("x")]}, sort=True)
+    assert out["x_min"].tolist() == [x[g == k].min() for k in range(5)]
+    np.testing.assert_allclose(out["x_sum"], [x[g == k].sum() for k in range(5)], rtol=1e-9)

@@ -415,9 +415,19 @@ class GroupBy:
         df = self.df
         descs, labels = [], []
         columns = dict(df.columns)
+        if isinstance(actions, str):  # df.groupby(by, agg='count') (vaex/groupby.py:688-700)
+            actions = [_agg.aggregates[actions]("*")] if actions == "count" else {c: actions for c in df.columns if c not in self.by}
         if isinstance(actions, dict):
             for col, names in actions.items():
+                if isinstance(names, _agg.AggregatorDescriptor):  # {'label': vaex.agg.mean('x')}: the key names the output column
+                    descs.append(names)
+                    labels.append(col)
+                    continue
                 for n in ([names] if isinstance(names, str) else names):
+                    if isinstance(n, _agg.AggregatorDescriptor):
+                        descs.append(n)
+                        labels.append(f"{col}_{n.short_name}")
+                        continue
                     # the moment aggregators take expression.astype('float64') like Frame.var/std do (vaex/agg.py:429-431)
                     src = df._as_float64(col, columns) if n in ("var", "std", "skew", "kurtosis") else col
                     descs.append(_agg.aggregates[n](src))
