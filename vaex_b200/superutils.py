@@ -422,7 +422,12 @@ def create_set_string(keys, null_index=-1, nan_count=0, null_count=0, fingerprin
     """vaex/hash.py:28-36: an ordered_set_string rebuilt from its keys in ordinal order (a pyarrow string array whose null slot, if
     any, is the null key) — one shard, so ordinal == position again."""
     s = ordered_set_string(1)
-    if len(keys):
+    # a null takes the ordinal at the END of the update call that first sees it (src/hash_string.hpp): feed the keys up to and
+    # including the null slot in one call, the rest in a second one, and every key is back at its position
+    if null_count and 0 <= null_index < len(keys) - 1:
+        s.update(keys[:null_index + 1])
+        s.update(keys[null_index + 1:])
+    elif len(keys):
         s.update(keys)
     s.fingerprint = fingerprint
     return s
