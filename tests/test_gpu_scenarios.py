@@ -121,3 +121,28 @@ def test_groupby_agg_argument_forms():
     out = df.groupby("g", agg={"x": ["min", agg.sum("x")]}, sort=True)
     assert out["x_min"].tolist() == [x[g == k].min() for k in range(5)]
     np.testing.assert_allclose(out["x_sum"], [x[g == k].sum() for k in range(5)], rtol=1e-9)
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_groupby_on_virtual_columns_and_expressions(device):
+    # tests/groupby_test.py:82-98: the key is a virtual column / an expression, evaluated on the device chunk by chunk
+    import torch
+    from vaex_b200.frame import Frame
+    rng = np.random.default_rng(10)
+    n = 25_000
+    k = rng.integers(0, 12, n).astype("i8")
+    v = rng.normal(0, 1, n)
+    cols = dict(k=k, v=v)
+    if device:
+        cols = {c: torch.from_numpy(a).cuda() for c, a in cols.items()}
+    df = Frame(cols)
+    df.add_virtual_column("kk", "k * 2 + 1")
+    for by in ("kk", "k * 2 + 1"):
+        out = df.groupby(by, agg={"v": ["sum", "count"]}, sort=True)
+        uniq = np.unique(k * 2 + 1)
+        assert np.array_equal(np.asarray(out[by]), uniq)
+        assert out["v_count"].tolist() == [int((k * 2 + 1 == u).sum()) for u in uniq]
+        np.testing.assert_allclose(out["v_sum"], [v[k * 2 + 1 == u].sum() for u in uniq], rtol=1e-9, atol=1e-12)
+    # a filtered frame keeps its filter through the groupby
+    out = df.filter("v > 0").groupby("kk", agg="count", sort=True)
+    assert out["count"].tolist() == [int(((k * 2 + 1 == u) & (v > 0)).sum()) for u in np.unique((k * 2 + 1)[v > 0])]

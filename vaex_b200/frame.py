@@ -335,8 +335,13 @@ class GroupBy:
         fewer than 10 rows per cell (vaex/groupby.py:653-668): the keys' ordinals are fused into one int64 code on the device
         (hash.CombinedCodes) and the groupby runs over the distinct codes — the reference's sparse `_combine` path
         (vaex/groupby.py:526-584)."""
-        self.df = df
         self.by = [by] if isinstance(by, str) else list(by)
+        if any(name not in df.columns for name in self.by):  # a key that is an expression: group by it as a virtual column
+            df = Frame(dict(df.columns), executor=df.executor, categories=df.categories, filter=df._filter_expression, variables=df.variables)
+            for name in self.by:
+                if name not in df.columns:
+                    df.add_virtual_column(name, name)
+        self.df = df
         self.fused = fused
         self.sort = sort
         self.combined = None
