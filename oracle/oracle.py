@@ -496,3 +496,44 @@ class StringOrderedSet:
                 m = string_hash(s.encode("utf8")) % self.nmaps
                 out[i] = off[m] + self.maps[m][s] if s in self.maps[m] else -1
         return out
+
+
+def agg_list(cells, values, valid=None, ncells=None, dropnan=False, dropnull=False, calls=None):
+    """AggListPrimitive (src/agg_list.cpp:84-113 aggregate, :47-83 get_result) restated: per cell of the flat grid the non-NaN values
+    of the valid rows in arrival order, then one NaN per NaN value (unless dropnan), then one slot per null row (unless dropnull).
+    `cells`: flat cell index per row; `valid`: 1 = use the row (the data mask the task part hands over, vaex/cpu.py:765-784), None =
+    all; `calls`: row ranges fed as separate bin() calls.  REFERENCE QUIRK, kept: aggregate() is called per 1024-row block of a
+    call with the block's offset applied to the data pointer but NOT to the mask (src/agg_list.cpp:96 `data_mask_ptr[j]` against
+    :97 `data_ptr[offset + j]`), so row r of a call is judged by mask[r % 1024] of that call — the same slip as AggFirst
+    (src/agg_first.cpp:131).  Returns
+    (offsets int64[ncells + 1], values, nan_count[ncells], null_count[ncells]); the null slots of `values` are unspecified in the
+    reference (uninitialised memory) and hold 0 here."""
+    cells = np.asarray(cells, dtype=np.int64)
+    values = np.asarray(values)
+    n = len(cells)
+    ncells = int(cells.max()) + 1 if ncells is None else int(ncells)
+    lists = [[] for _ in range(ncells)]
+    nan_count, null_count = np.zeros(ncells, np.int64), np.zeros(ncells, np.int64)
+    isf = values.dtype.kind == "f"
+    for i1, i2 in (calls or [(0, n)]):
+        for j in range(i1, i2):
+            c = int(cells[j])
+            jm = i1 + (j - i1) % 1024  # the mask entry the reference looks at
+            if valid is None or valid[jm] == 1:
+                v = values[j]
+                if not isf or v == v:
+                    lists[c].append(v)
+                elif not dropnan:
+                    nan_count[c] += 1
+            elif valid is not None and valid[jm] == 0 and not dropnull:
+                null_count[c] += 1
+    offsets = np.zeros(ncells + 1, np.int64)
+    for c in range(ncells):
+        offsets[c + 1] = offsets[c] + len(lists[c]) + nan_count[c] + null_count[c]
+    out = np.zeros(int(offsets[-1]), values.dtype.newbyteorder("="))
+    for c in range(ncells):
+        k = len(lists[c])
+        out[offsets[c]:offsets[c] + k] = lists[c]
+        if nan_count[c]:
+            out[offsets[c] + k:offsets[c] + k + nan_count[c]] = np.nan
+    return offsets, out, nan_count, null_count

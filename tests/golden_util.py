@@ -74,3 +74,20 @@ def load_strings():
         name, field = key.split("/", 1)
         cases.setdefault(name, {})[field] = z[key]
     return cases
+
+
+AGGLIST_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "agglist_golden.npz")
+
+
+def load_agglist():
+    """tests/golden/agglist_golden.npz (tests/golden/make_golden_agglist.py): the shared key column `x` (ordinal binner, `ncat`
+    categories), the row where the second bin() call starts (`cut`), per dtype the value column and the data mask, and per case
+    ('<dtype>/<plain|masked>_dropnan<0|1>_dropnull<0|1>') the (offsets, values) the compiled reference's AggList returned."""
+    z = np.load(AGGLIST_PATH, allow_pickle=False)
+    cases = {}
+    for key in z.files:
+        if key.endswith("/offsets"):
+            dt, case, _ = key.split("/")
+            cases[f"{dt}/{case}"] = dict(dtype=dt, masked=case.startswith("masked"), dropnan="dropnan1" in case, dropnull="dropnull1" in case,
+                                         offsets=z[key], values=z[f"{dt}/{case}/values"], v=z[f"{dt}/v"], valid=z[f"{dt}/valid"])
+    return dict(x=z["x"], ncat=int(z["ncat"]), cut=int(z["cut"]), cases=cases)

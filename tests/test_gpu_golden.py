@@ -68,3 +68,28 @@ def test_minmax_matches_golden(name, device):
     assert np.array_equal(got_raw, raw, equal_nan=True), (name, got_raw, raw)
     got = df.minmax("v")
     assert got.dtype == result.dtype and np.array_equal(got, result, equal_nan=True)
+
+
+AGGLIST = golden_util.load_agglist()
+
+
+@pytest.mark.parametrize("name", sorted(AGGLIST["cases"]))
+def test_agg_list_matches_golden(name):
+    """superagg.AggList_<dtype>_int64 (csrc/list.cu) against the compiled reference's vectors: same two bin() calls, offsets and
+    values bit-identical (NaN slots are NaN; the NULL slots are unspecified in the reference and zero in the file and on the device)."""
+    from vaex_b200 import superagg
+    c = AGGLIST["cases"][name]
+    x, cut = AGGLIST["x"], AGGLIST["cut"]
+    n = len(x)
+    b = superagg.BinnerOrdinal_int32(1, "x", AGGLIST["ncat"], 0, False, False)
+    g = superagg.Grid([b])
+    a = getattr(superagg, f"AggList_{c['dtype']}_int64")(g, 1, 1, c["dropnan"], c["dropnull"])
+    for i1, i2 in ((0, cut), (cut, n)):
+        b.set_data(0, np.ascontiguousarray(x[i1:i2]))
+        a.set_data(0, np.ascontiguousarray(c["v"][i1:i2]), 0)
+        if c["masked"]:
+            a.set_data_mask(0, np.ascontiguousarray(c["valid"][i1:i2]))
+        g.bin(0, [a], i2 - i1)
+    offsets, values = a.result_arrays()
+    assert np.array_equal(offsets, c["offsets"])
+    assert values.dtype == c["values"].dtype and np.array_equal(values, c["values"], equal_nan=True)

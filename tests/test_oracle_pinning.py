@@ -152,3 +152,20 @@ def test_oracle_string_set_matches_golden(name, oracle):
     probe = golden_util.unpack_strings(c["probe_offsets"], c["probe_bytes"], c["probe_mask"])
     assert np.array_equal(s.map_ordinal(probe), c["probe_ordinals"])
     assert [len(s), s.null_count, s.null_index] == c["info"].tolist()
+
+
+def test_agg_list_restatement_matches_the_compiled_reference_vectors():
+    """oracle.agg_list (src/agg_list.cpp restated, incl. the mask-without-block-offset quirk) against the vectors the compiled
+    reference's AggList_<dtype>_int64 produced (tests/golden/make_golden_agglist.py): 5 dtypes x plain / masked x dropnan x dropnull,
+    fed in two calls of 1777 and 2223 rows (so the 1024-row blocks and the call boundary both matter)."""
+    import golden_util
+    from oracle import oracle as O
+    g = golden_util.load_agglist()
+    x, n = g["x"], len(g["x"])
+    cells = O.flat_indices([O.ordinal(x, g["ncat"], 0)], n)[0].astype(np.int64)
+    assert len(g["cases"]) == 40
+    for name, c in g["cases"].items():
+        off, vals, _, _ = O.agg_list(cells, c["v"], c["valid"] if c["masked"] else None, len(c["offsets"]) - 1, c["dropnan"], c["dropnull"],
+                                     calls=[(0, g["cut"]), (g["cut"], n)])
+        assert np.array_equal(off, c["offsets"]), name
+        assert np.array_equal(vals, c["values"], equal_nan=True), name

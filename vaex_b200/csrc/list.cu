@@ -42,8 +42,11 @@ __global__ void __launch_bounds__(256) k_list_append(const __grid_constant__ Lis
         uint64_t r[4] = {0, 0, 0, 0};
         unsigned m[4] = {1, 1, 1, 1};
         load4_raw<VEC>(p.data, p.isz, base, nv, r);
+        // REFERENCE QUIRK, kept (golden vectors from the compiled reference pin it): AggListPrimitive::aggregate runs per 1024-row
+        // block of a bin() call with the block offset applied to the data but NOT to the mask (src/agg_list.cpp:96-97), so row r of
+        // a call is judged by mask[r % 1024] — the same slip as AggFirst (src/agg_first.cpp:131).  base is a multiple of 4.
         if (p.mask)
-            load4_mask<VEC>(p.mask, base, nv, m);
+            load4_mask<VEC>(p.mask, base & 1023, nv, m);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             if (j >= nv)
